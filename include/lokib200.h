@@ -1,0 +1,193 @@
+/* include/lokib200.h -- C ABI of the B200-native electron Monte Carlo engine (liblokib200.so).
+ *
+ * This is the drop-in boundary for LoKI-MC's data-parallel hot path.  The reference (IST-Lisbon/LoKI-MC v1.1.0) has no
+ * plugin/FFI interface; the cut is made INSIDE BoltzmannMC::evaluateEEDF(), file Code/LoKI-MC/Sources/BoltzmannMC.C
+ * ("BMC.C" below; "BMC.h" = Headers/BoltzmannMC.h).  Each entry point names the reference code it replaces.
+ * Conventions: plain pointers and sizes only; every function returns 0 on success or a negative lokib200_status and never
+ * calls exit() (the reference's Message::error convention, Sources/Message.C:6-16, is applied by the host from
+ * lokib200_last_error()).  The engine owns all device memory; the caller owns every pointer it passes and may free it on
+ * return.  One engine = one job on one GPU; call from one host thread.  Units are SI except energies (eV), as in the reference.
+ */
+#ifndef LOKIB200_H
+#define LOKIB200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LOKIB200_ABI_VERSION 1
+#define LOKIB200_NON_DEF (-123456789.0)    /* Headers/Constant.h:23 */
+#define LOKIB200_NULL_COLLISION (-1)       /* Headers/GeneralDefinitions.h:39 */
+#define LOKIB200_PARTIAL_FLIGHT (-2)       /* Headers/GeneralDefinitions.h:40 */
+
+typedef enum lokib200_status {
+  LOKIB200_OK = 0,
+  LOKIB200_ERR_INVALID = -1,      /* bad argument / call order */
+  LOKIB200_ERR_CUDA = -2,         /* CUDA runtime failure (message in last_error) */
+  LOKIB200_ERR_NO_DEVICE = -3,    /* no usable sm_100 device: there is NO CPU fallback */
+  LOKIB200_ERR_OVERFLOW = -4,     /* birth list overflow inside one interval */
+  LOKIB200_ERR_ENERGY_RANGE = -5  /* electron energy beyond the elastic cross-section range (BMC.C:1427-1430) */
+} lokib200_status;
+
+typedef struct lokib200_engine lokib200_engine;
+
+/* Job constants: what BoltzmannMC's constructor (BMC.h:244-380) and evaluateNonConstantVariables (BMC.C:428-489) hold. */
+typedef struct lokib200_config {
+  int64_t n_electrons;              /* electrons of THIS shard (BMC.h:51) */
+  uint64_t seed;                    /* Philox key; draw streams are keyed by the GLOBAL electron id */
+  uint64_t first_electron_id;       /* global id of local electron 0 (shard offset); 0 on a single GPU */
+  int32_t device;                   /* CUDA device ordinal */
+  int32_t gas_temperature_effect;   /* 0 false, 1 true, 2 smartActivation (GeneralDefinitions.h:49-51) */
+  int32_t ionization_sharing;       /* 0 equalSharing, 1 oneTakesAll, 2 usingSDCS, 3 randomUniform (GeneralDefinitions.h:43-46) */
+  int32_t is_cylindrically_symmetric; /* WorkingConditions.h:164-172: EVDF / angular histograms only when E || z */
+  double energy_sharing_factor;     /* BMC.h:53 */
+  double gas_density;               /* totalGasDensity [m^-3] (BMC.C:436) */
+  double gas_temperature;           /* [K] */
+  double electric_field[3];         /* [V/m], BMC.C:465-481 (AC amplitude already multiplied by sqrt(2)) */
+  double excitation_omega;          /* excitationFrequencyRadians [rad/s] (BMC.C:477) */
+  double cyclotron_omega;           /* cyclotronFrequency [rad/s] (BMC.C:485) */
+  int32_t n_interp_points;          /* interpolCrossSectionSize (BMC.h:104), default 10000 */
+  int32_t n_energy_cells;           /* BMC.h:59  (1000) */
+  int32_t n_cos_cells;              /* BMC.h:60  (100)  */
+  int32_t n_radial_cells;           /* BMC.h:62  (200)  */
+  int32_t n_axial_cells;            /* BMC.h:61  (200)  */
+  int32_t n_phases;                 /* nIntegrationPhases (BMC.h:75), used when excitation_omega != 0 */
+  int32_t reserved;
+} lokib200_config;
+
+/* Flattened process set: the per-process arrays BoltzmannMC::allocateEvaluateVariablesFirstTime fills (BMC.C:89-270).
+ * Inelastic and superelastic directions are separate processes; a superelastic follows its inelastic (BMC.C:209-266). */
+typedef struct lokib200_process_soa {
+  int32_t n_processes;                       /* nProcesses (BMC.C:33-48) */
+  int32_t n_gases;                           /* nGases */
+  const int32_t* type;                       /* processTypes: 0 conservative, 1 ionization, 2 attachment */
+  const int32_t* is_superelastic;            /* isSuperElastic */
+  const int32_t* angular_model;              /* 0 isotropic 1 forward 2 bornDipole 3 surendra 4 coulombScreen 5 momentumConservationIonization
+                                                (Headers/AngularScatteringFunctions.h:76-114) */
+  const double* angular_p0;                  /* angularScatteringParams[k][0] (coulombScreen energy option) */
+  const double* angular_p1;                  /* angularScatteringParams[k][1] (coulombScreen screening energy [eV]) */
+  const double* superelastic_weight_factor;  /* superElasticStatWeightFactors */
+  const double* energy_min;                  /* energyMinLimits [eV] */
+  const double* energy_max;                  /* energyMaxLimits [eV] */
+  const double* rel_density;                 /* relDensities (BMC.C:446-452) */
+  const double* target_mass;                 /* targetMasses [kg] */
+  const double* reduced_mass;                /* reducedMasses [kg] */
+  const double* energy_loss;                 /* energyLosses [eV] (negative for superelastics, BMC.C:247) */
+  const double* thermal_std;                 /* thermalStdDeviations sqrt(kB Tg / M) [m/s] */
+  const double* w_parameter;                 /* wParameters [eV] (BMC.C:173-183) */
+  const int32_t* gas_first;                  /* firstProcessIndexPerGas [n_gases] */
+  const int32_t* gas_last;                   /* lastProcessIndexPerGas  [n_gases] */
+  const double* gas_fraction;                /* gasFractions [n_gases] */
+  const int64_t* xs_offset;                  /* [n_processes+1]: process k owns raw points [xs_offset[k], xs_offset[k+1]) */
+  const double* xs_energy;                   /* crossSectionEnergies, concatenated [eV] */
+  const double* xs_value;                    /* crossSectionValues, concatenated [m^2] */
+} lokib200_process_soa;
+
+/* What one advance returns to the host: everything nonParallelCollisionTasks (BMC.C:1282-1408) and
+ * calculateMeanDataForSwarmParams (BMC.C:1410-1454) accumulate, as SUMS over this shard (so that shards combine by addition;
+ * see INTEGRATION.md for the NCCL all-reduce layout).  Stored as doubles; integer-valued entries are exact below 2^53. */
+enum {
+  LOKIB200_R_N_REAL = 0,       /* totalCollisionCounter increment */
+  LOKIB200_R_N_NULL = 1,       /* nullCollisionCounter increment */
+  LOKIB200_R_N_BORN = 2,       /* ionization events (ejected electrons) */
+  LOKIB200_R_N_ATTACHED = 3,   /* attachment events */
+  LOKIB200_R_GAIN_FIELD = 4,   /* energyGainField increment [eV] */
+  LOKIB200_R_GROWTH = 5,       /* energyGrowth increment [eV] */
+  LOKIB200_R_SUM_EPS = 6,      /* sum of energies at t_sync [eV] */
+  LOKIB200_R_SUM_R = 7,        /* 3: sum r */
+  LOKIB200_R_SUM_V = 10,       /* 3: sum v */
+  LOKIB200_R_SUM_RR = 13,      /* 9: sum r r^T (row-major xx xy xz yx ...) */
+  LOKIB200_R_SUM_RV = 22,      /* 9: sum r v^T */
+  LOKIB200_R_N_SAMPLED = 31,   /* electrons in the sums (= n_electrons) */
+  LOKIB200_R_N_TABLE_CLAMPED = 32, /* collisions whose energy index hit the last table row (BMC.C:955,1038 clamp) */
+  LOKIB200_R_N_NU_EXCEEDED = 33,   /* collisions that found nu_tot(eps) > nu_e (trial frequency too small) */
+  LOKIB200_R_SUM_COUNT = 34,   /* --- entries below combine with MAX, not SUM --- */
+  LOKIB200_R_MAX_EPS = 34,     /* max energy at t_sync [eV] (BMC.C:721, :1426) */
+  LOKIB200_R_MAX_EPS_SEEN = 35,/* max energy seen at any collision point inside the interval */
+  LOKIB200_R_HEADER = 36       /* followed by counts[P], gain[P], loss[P] (collisionCounters, energyGain/LossProcesses) : SUM */
+};
+#define LOKIB200_RESULT_LEN(P) (LOKIB200_R_HEADER + 3 * (P))
+
+/* one electron for the injected-draw parity entry: the per-electron slice of BMC.h:148-153,133-134 */
+typedef struct lokib200_electron {
+  double r[3], v[3];
+  double energy;    /* electronEnergies [eV] */
+  double t;         /* electronTimes [s] */
+  double t_cf;      /* collisionFreeTimes [s]; LOKIB200_NON_DEF = draw a new one */
+  double nu_e;      /* trialCollisionFrequenciesEachElectron [1/s] */
+} lokib200_electron;
+
+/* scratch the parallel pass hands to the serial pass in the reference (BMC.h:226-231) */
+typedef struct lokib200_event_out {
+  int32_t chosen;   /* chosenProcessIDs */
+  int32_t draws_used;
+  double dE;        /* electronEnergyChanges [eV] */
+  double dE_rel;    /* electronEnergyChangesOverIncidEnergies */
+  double gain_field;/* energyGainsField [eV] */
+  double ej_r[3], ej_v[3], ej_energy;   /* ejectedElectron{Positions,Velocities,Energies} */
+} lokib200_event_out;
+
+int lokib200_abi_version(void);
+int lokib200_device_count(void);
+
+/* --- life cycle (replaces: BoltzmannMC ctor allocations BMC.C:51-87; the reference never frees) --- */
+int lokib200_create(const lokib200_config* cfg, lokib200_engine** out);
+void lokib200_destroy(lokib200_engine* h);
+const char* lokib200_last_error(const lokib200_engine* h);   /* h may be NULL: error of the last failed create */
+/* run on an existing stream (cudaStream_t as void*), e.g. torch's current stream; NULL -> engine-owned stream */
+int lokib200_set_stream(lokib200_engine* h, void* cuda_stream);
+
+/* --- tables (replaces: allocateEvaluateVariablesFirstTime BMC.C:89-270 hand-off, interpolateCrossSections BMC.C:561-615) --- */
+int lokib200_set_processes(lokib200_engine* h, const lokib200_process_soa* p);
+/* host flattening + upload: uniform grid of n_interp_points energies up to max_energy, sigma x relDensity, row cumsum, nu_tot, running max */
+int lokib200_build_tables(lokib200_engine* h, double max_energy);
+/* upload tables built elsewhere (e.g. dumped from the reference object); cum is row-major [nE][P] */
+int lokib200_upload_tables(lokib200_engine* h, const double* cum, const double* nu_tot, const double* nu_max, int32_t nE, double dE);
+int lokib200_get_tables(lokib200_engine* h, double* cum, double* nu_tot, double* nu_max);   /* device -> host, any may be NULL */
+int lokib200_table_info(const lokib200_engine* h, int32_t* nE, double* dE, double* max_energy, double* nu_max_last);
+double lokib200_nu_max_at(const lokib200_engine* h, int32_t index);   /* maxCollisionFrequencies[index] (BMC.C:755) */
+
+/* --- ensemble state (replaces: evaluateNonConstantVariables BMC.C:491-516) --- */
+int lokib200_init_ensemble(lokib200_engine* h, double initial_temp_over_gas_temp, double* max_energy);
+/* soa8 = x,y,z,vx,vy,vz,t_cf,nu_e each [n_electrons] (host memory).  time = common clock of the ensemble. */
+int lokib200_set_ensemble(lokib200_engine* h, const double* soa8, double time);
+int lokib200_get_ensemble(lokib200_engine* h, double* soa8);
+double lokib200_time(const lokib200_engine* h);
+
+/* --- the hot path (replaces: electronDynamicsUntilSynchronization BMC.C:617-688 incl. accelerateElectron :804-905,
+ *     performCollision :907-1113, conservative/ionization/attachmentCollision :1115-1280, nonParallelCollisionTasks :1282-1408,
+ *     and, when `sample` != 0, the ensemble sums of calculateMeanDataForSwarmParams :1410-1454) ---
+ * Advances every electron from the engine's time to t_sync with trial frequency nu_trial, applies birth/death population
+ * control at t_sync, and writes LOKIB200_RESULT_LEN(P) doubles to `result` (host memory; may be NULL). */
+int lokib200_advance_to_sync(lokib200_engine* h, double nu_trial, double t_sync, int32_t sample, double* result);
+/* same, asynchronous: the result stays in device memory (`d_result`, >= LOKIB200_RESULT_LEN(P) doubles, caller-owned device
+ * pointer, e.g. a torch tensor that is then all-reduced over NCCL); no host synchronisation */
+int lokib200_advance_to_sync_device(lokib200_engine* h, double nu_trial, double t_sync, int32_t sample, double* d_result);
+
+/* --- distributions (replaces: getTimeDependDistributions BMC.C:1492-1572, histogramCount / histogram2DCount MathFunctions.C:61-127) ---
+ * grids are those of checkSteadyState (BMC.C:1862-1883): energy [0,max_eedf_energy], cos in [-1,1], v_r in [0,v_max], v_z in [-v_max,v_max] */
+int lokib200_set_histogram_grid(lokib200_engine* h, double max_eedf_energy);   /* also zeroes the accumulators */
+int lokib200_sample_histograms(lokib200_engine* h, int32_t phase_index);        /* phase_index < 0: no phase-resolved EEDF */
+/* accumulated counts as doubles (eehSum [nE], eahSum [nE][nCos], evhSum [nR][nA], eehSum_periodic [nPhases][nE]); any may be NULL */
+int lokib200_fetch_histograms(lokib200_engine* h, double* eeh, double* eah, double* evh, double* eeh_periodic);
+
+/* --- injected-draw parity entry: n independent electrons, one pass of the loop body BMC.C:637-681 each, executed by the SAME
+ *     device functions as lokib200_advance_to_sync.  draws is [n][n_draws] --- */
+int lokib200_step_injected(lokib200_engine* h, int32_t n, const lokib200_electron* in, double nu_trial, const double* t_sync,
+                           const double* draws, int32_t n_draws, lokib200_electron* out, lokib200_event_out* ev);
+
+/* --- helpers that mirror host-side scalar logic of the path --- */
+/* maximizationAccelerationEnergy (BMC.C:765-802) */
+double lokib200_max_accel_energy(const lokib200_engine* h, double initial_energy, double dt);
+/* checkMaxCollisionFrequency (BMC.C:716-763): may rebuild tables; returns the (possibly raised) trial frequency through *nu_trial */
+int lokib200_check_nu_trial(lokib200_engine* h, double max_energy, double horizon, double energy_max_elastic, double* nu_trial);
+/* number of kernels launched by this engine so far (bench.py's gpu_launches) */
+int64_t lokib200_launch_count(const lokib200_engine* h);
+/* average device time [ms] of the advance kernel over the launches since the last call (CUDA events on the engine's stream) */
+int lokib200_kernel_time_ms(lokib200_engine* h, double* advance_ms, int64_t* launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

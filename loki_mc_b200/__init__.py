@@ -1,0 +1,6 @@
+"""loki_mc_b200 -- B200-native engine for LoKI-MC's electron Monte Carlo hot path.
+
+The product is liblokib200.so (CUDA kernels + C ABI, include/lokib200.h).  This package is the thin Python binding the tests
+and bench.py use; it never falls back to a CPU implementation: importing works without a GPU, creating an Engine does not.
+"""
+from ._capi import Engine, LokiB200Error, build, lib, lib_path, result_len, R  # noqa: F401

@@ -1,0 +1,269 @@
+"""ctypes binding of include/lokib200.h (liblokib200.so).  No compute happens here."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(PKG)
+SRC = os.path.join(PKG, "csrc")
+ND = -123456789.0
+
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-fmad=false", "-std=c++17", "-Xcompiler", "-fPIC", "-shared"]
+
+
+class LokiB200Error(RuntimeError):
+    pass
+
+
+class R:
+    """indices of the result vector (LOKIB200_R_* in include/lokib200.h)"""
+    N_REAL, N_NULL, N_BORN, N_ATTACHED, GAIN_FIELD, GROWTH, SUM_EPS, SUM_R, SUM_V, SUM_RR, SUM_RV = 0, 1, 2, 3, 4, 5, 6, 7, 10, 13, 22
+    N_SAMPLED, N_TABLE_CLAMPED, N_NU_EXCEEDED, SUM_COUNT, MAX_EPS, MAX_EPS_SEEN, HEADER = 31, 32, 33, 34, 34, 35, 36
+
+
+def result_len(P):
+    return R.HEADER + 3 * P
+
+
+def lib_path():
+    return os.path.join(PKG, "liblokib200.so")
+
+
+def build(force=False, verbose=False):
+    """Compile csrc/lokib200.cu for sm_100a into loki_mc_b200/liblokib200.so (in-tree, so it travels to the GPU box)."""
+    out = lib_path()
+    srcs = [os.path.join(SRC, f) for f in ("lokib200.cu", "lk_kernels.cuh", "lk_physics.cuh")] + [os.path.join(ROOT, "include", "lokib200.h")]
+    if not force and os.path.exists(out) and all(os.path.getmtime(out) >= os.path.getmtime(s) for s in srcs):
+        return out
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", out, srcs[0]]
+    subprocess.check_call(cmd)
+    return out
+
+
+class Config(C.Structure):
+    _fields_ = [("n_electrons", C.c_int64), ("seed", C.c_uint64), ("first_electron_id", C.c_uint64), ("device", C.c_int32),
+                ("gas_temperature_effect", C.c_int32), ("ionization_sharing", C.c_int32), ("is_cylindrically_symmetric", C.c_int32),
+                ("energy_sharing_factor", C.c_double), ("gas_density", C.c_double), ("gas_temperature", C.c_double),
+                ("electric_field", C.c_double * 3), ("excitation_omega", C.c_double), ("cyclotron_omega", C.c_double),
+                ("n_interp_points", C.c_int32), ("n_energy_cells", C.c_int32), ("n_cos_cells", C.c_int32), ("n_radial_cells", C.c_int32),
+                ("n_axial_cells", C.c_int32), ("n_phases", C.c_int32), ("reserved", C.c_int32)]
+
+
+c_dp = C.POINTER(C.c_double)
+c_ip = C.POINTER(C.c_int32)
+c_lp = C.POINTER(C.c_int64)
+
+
+class ProcessSoA(C.Structure):
+    _fields_ = [("n_processes", C.c_int32), ("n_gases", C.c_int32), ("type", c_ip), ("is_superelastic", c_ip), ("angular_model", c_ip),
+                ("angular_p0", c_dp), ("angular_p1", c_dp), ("superelastic_weight_factor", c_dp), ("energy_min", c_dp), ("energy_max", c_dp),
+                ("rel_density", c_dp), ("target_mass", c_dp), ("reduced_mass", c_dp), ("energy_loss", c_dp), ("thermal_std", c_dp),
+                ("w_parameter", c_dp), ("gas_first", c_ip), ("gas_last", c_ip), ("gas_fraction", c_dp), ("xs_offset", c_lp),
+                ("xs_energy", c_dp), ("xs_value", c_dp)]
+
+
+ELECTRON_DTYPE = np.dtype([("r", "f8", 3), ("v", "f8", 3), ("energy", "f8"), ("t", "f8"), ("t_cf", "f8"), ("nu_e", "f8")])
+EVENT_DTYPE = np.dtype([("chosen", "i4"), ("draws_used", "i4"), ("dE", "f8"), ("dE_rel", "f8"), ("gain_field", "f8"), ("ej_r", "f8", 3),
+                        ("ej_v", "f8", 3), ("ej_energy", "f8")])
+
+_LIB = None
+# every symbol include/lokib200.h declares (tests check they are all exported)
+SYMBOLS = ["lokib200_abi_version", "lokib200_device_count", "lokib200_create", "lokib200_destroy", "lokib200_last_error", "lokib200_set_stream",
+           "lokib200_set_processes", "lokib200_build_tables", "lokib200_upload_tables", "lokib200_get_tables", "lokib200_table_info",
+           "lokib200_nu_max_at", "lokib200_init_ensemble", "lokib200_set_ensemble", "lokib200_get_ensemble", "lokib200_time",
+           "lokib200_advance_to_sync", "lokib200_advance_to_sync_device", "lokib200_set_histogram_grid", "lokib200_sample_histograms",
+           "lokib200_fetch_histograms", "lokib200_step_injected", "lokib200_max_accel_energy", "lokib200_check_nu_trial",
+           "lokib200_launch_count", "lokib200_kernel_time_ms"]
+
+
+def lib():
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = lib_path()
+    if not os.path.exists(path):
+        raise LokiB200Error("liblokib200.so is not built (run `python -c 'import __graft_entry__ as g; g.build()'`); there is no CPU fallback")
+    L = C.CDLL(path)
+    vp = C.c_void_p
+    L.lokib200_create.argtypes = [C.POINTER(Config), C.POINTER(vp)]
+    L.lokib200_destroy.argtypes = [vp]; L.lokib200_destroy.restype = None
+    L.lokib200_last_error.argtypes = [vp]; L.lokib200_last_error.restype = C.c_char_p
+    L.lokib200_set_stream.argtypes = [vp, vp]
+    L.lokib200_set_processes.argtypes = [vp, C.POINTER(ProcessSoA)]
+    L.lokib200_build_tables.argtypes = [vp, C.c_double]
+    L.lokib200_upload_tables.argtypes = [vp, c_dp, c_dp, c_dp, C.c_int32, C.c_double]
+    L.lokib200_get_tables.argtypes = [vp, c_dp, c_dp, c_dp]
+    L.lokib200_table_info.argtypes = [vp, c_ip, c_dp, c_dp, c_dp]
+    L.lokib200_nu_max_at.argtypes = [vp, C.c_int32]; L.lokib200_nu_max_at.restype = C.c_double
+    L.lokib200_init_ensemble.argtypes = [vp, C.c_double, c_dp]
+    L.lokib200_set_ensemble.argtypes = [vp, c_dp, C.c_double]
+    L.lokib200_get_ensemble.argtypes = [vp, c_dp]
+    L.lokib200_time.argtypes = [vp]; L.lokib200_time.restype = C.c_double
+    L.lokib200_advance_to_sync.argtypes = [vp, C.c_double, C.c_double, C.c_int32, c_dp]
+    L.lokib200_advance_to_sync_device.argtypes = [vp, C.c_double, C.c_double, C.c_int32, vp]
+    L.lokib200_set_histogram_grid.argtypes = [vp, C.c_double]
+    L.lokib200_sample_histograms.argtypes = [vp, C.c_int32]
+    L.lokib200_fetch_histograms.argtypes = [vp, c_dp, c_dp, c_dp, c_dp]
+    L.lokib200_step_injected.argtypes = [vp, C.c_int32, vp, C.c_double, c_dp, c_dp, C.c_int32, vp, vp]
+    L.lokib200_max_accel_energy.argtypes = [vp, C.c_double, C.c_double]; L.lokib200_max_accel_energy.restype = C.c_double
+    L.lokib200_check_nu_trial.argtypes = [vp, C.c_double, C.c_double, C.c_double, c_dp]
+    L.lokib200_launch_count.argtypes = [vp]; L.lokib200_launch_count.restype = C.c_int64
+    L.lokib200_kernel_time_ms.argtypes = [vp, c_dp, c_lp]
+    _LIB = L
+    return L
+
+
+def _dp(a):
+    return a.ctypes.data_as(c_dp)
+
+
+class Engine:
+    """One job on one GPU.  `model` is a dict with the process SoA ('p_*', 'gas_*', 'xs_*') and 'cond' (job conditions),
+    the same layout tests/golden_io.load returns."""
+
+    def __init__(self, model, n_electrons, seed=0x4C6F4B49, device=0, first_electron_id=0, n_phases=100, cells=(1000, 100, 200, 200)):
+        L = lib()
+        self.L = L
+        c = model["cond"]
+        cfg = Config()
+        cfg.n_electrons = int(n_electrons); cfg.seed = int(seed); cfg.first_electron_id = int(first_electron_id); cfg.device = int(device)
+        cfg.gas_temperature_effect = int(c["gas_temperature_effect"]); cfg.ionization_sharing = int(c["ionization_sharing"])
+        cfg.is_cylindrically_symmetric = int(c.get("is_cylindrically_symmetric", 1))
+        cfg.energy_sharing_factor = float(c["energy_sharing_factor"]); cfg.gas_density = float(c["gas_density"])
+        cfg.gas_temperature = float(c["gas_temperature"])
+        for i in range(3):
+            cfg.electric_field[i] = float(c["electric_field"][i])
+        cfg.excitation_omega = float(c["excitation_omega"]); cfg.cyclotron_omega = float(c["cyclotron_omega"])
+        cfg.n_interp_points = int(c.get("n_interp_points", 10000))
+        cfg.n_energy_cells, cfg.n_cos_cells, cfg.n_radial_cells, cfg.n_axial_cells = (int(x) for x in cells)
+        cfg.n_phases = int(n_phases)
+        self.cfg = cfg
+        self.n = int(n_electrons)
+        self.energy_max_elastic = float(c.get("energy_max_elastic", 1e100))
+        h = C.c_void_p()
+        rc = L.lokib200_create(C.byref(cfg), C.byref(h))
+        if rc != 0:
+            raise LokiB200Error("lokib200_create failed (%d): %s" % (rc, L.lokib200_last_error(None).decode()))
+        self.h = h
+        i32 = lambda a: np.ascontiguousarray(a, dtype=np.int32)
+        f64 = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+        self.P = int(len(model["p_type"])); self.nG = int(len(model["gas_first"]))
+        k = dict(type=i32(model["p_type"]), sup=i32(model["p_superelastic"]), ang=i32(model["p_angular"]), ap0=f64(model["p_ap0"]),
+                 ap1=f64(model["p_ap1"]), swf=f64(model["p_swf"]), emin=f64(model["p_emin"]), emax=f64(model["p_emax"]),
+                 rd=f64(model["p_reldens"]), mass=f64(model["p_mass"]), mu=f64(model["p_redmass"]), el=f64(model["p_eloss"]),
+                 th=f64(model["p_thstd"]), w=f64(model["p_w"]), gf=i32(model["gas_first"]), gl=i32(model["gas_last"]),
+                 gfr=f64(model["gas_fraction"]), xo=np.ascontiguousarray(model["xs_offset"], dtype=np.int64), xe=f64(model["xs_energy"]),
+                 xv=f64(model["xs_value"]))
+        self._keep = k
+        ip = lambda a: a.ctypes.data_as(c_ip)
+        soa = ProcessSoA(self.P, self.nG, ip(k["type"]), ip(k["sup"]), ip(k["ang"]), _dp(k["ap0"]), _dp(k["ap1"]), _dp(k["swf"]), _dp(k["emin"]),
+                         _dp(k["emax"]), _dp(k["rd"]), _dp(k["mass"]), _dp(k["mu"]), _dp(k["el"]), _dp(k["th"]), _dp(k["w"]), ip(k["gf"]),
+                         ip(k["gl"]), _dp(k["gfr"]), k["xo"].ctypes.data_as(c_lp), _dp(k["xe"]), _dp(k["xv"]))
+        self._check(L.lokib200_set_processes(self.h, C.byref(soa)))
+
+    def _check(self, rc):
+        if rc != 0:
+            raise LokiB200Error("lokib200 error %d: %s" % (rc, self.L.lokib200_last_error(self.h).decode()))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.lokib200_destroy(self.h); self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # --- tables ---
+    def build_tables(self, max_energy):
+        self._check(self.L.lokib200_build_tables(self.h, float(max_energy)))
+
+    def upload_tables(self, cum, nu_tot, nu_max, dE):
+        cum = np.ascontiguousarray(cum, dtype=np.float64); nE = cum.shape[0]
+        self._check(self.L.lokib200_upload_tables(self.h, _dp(cum), _dp(np.ascontiguousarray(nu_tot)), _dp(np.ascontiguousarray(nu_max)), nE, float(dE)))
+
+    def table_info(self):
+        nE = C.c_int32(); dE = C.c_double(); mE = C.c_double(); nm = C.c_double()
+        self._check(self.L.lokib200_table_info(self.h, C.byref(nE), C.byref(dE), C.byref(mE), C.byref(nm)))
+        return dict(nE=nE.value, dE=dE.value, max_energy=mE.value, nu_max_last=nm.value)
+
+    def get_tables(self):
+        nE = self.table_info()["nE"]
+        cum = np.zeros((nE, self.P)); nt = np.zeros(nE); nm = np.zeros(nE)
+        self._check(self.L.lokib200_get_tables(self.h, _dp(cum), _dp(nt), _dp(nm)))
+        return cum, nt, nm
+
+    # --- ensemble ---
+    def init_ensemble(self, temp_ratio=0.01):
+        mx = C.c_double()
+        self._check(self.L.lokib200_init_ensemble(self.h, float(temp_ratio), C.byref(mx)))
+        return mx.value
+
+    def set_ensemble(self, soa8, time=0.0):
+        a = np.ascontiguousarray(soa8, dtype=np.float64); assert a.shape == (8, self.n)
+        self._check(self.L.lokib200_set_ensemble(self.h, _dp(a), float(time)))
+
+    def get_ensemble(self):
+        a = np.zeros((8, self.n))
+        self._check(self.L.lokib200_get_ensemble(self.h, _dp(a)))
+        return a
+
+    @property
+    def time(self):
+        return self.L.lokib200_time(self.h)
+
+    # --- hot path ---
+    def advance(self, nu_trial, t_sync, sample=True):
+        res = np.zeros(result_len(self.P))
+        self._check(self.L.lokib200_advance_to_sync(self.h, float(nu_trial), float(t_sync), int(bool(sample)), _dp(res)))
+        return res
+
+    def advance_device(self, nu_trial, t_sync, sample, d_result_ptr):
+        self._check(self.L.lokib200_advance_to_sync_device(self.h, float(nu_trial), float(t_sync), int(bool(sample)), C.c_void_p(d_result_ptr)))
+
+    def set_stream(self, stream_ptr):
+        self._check(self.L.lokib200_set_stream(self.h, C.c_void_p(stream_ptr)))
+
+    def step_injected(self, electrons, nu_trial, t_sync, draws):
+        e = np.ascontiguousarray(electrons, dtype=ELECTRON_DTYPE); n = len(e)
+        d = np.ascontiguousarray(draws, dtype=np.float64); assert d.shape[0] == n
+        ts = np.ascontiguousarray(t_sync, dtype=np.float64)
+        out = np.zeros(n, dtype=ELECTRON_DTYPE); ev = np.zeros(n, dtype=EVENT_DTYPE)
+        self._check(self.L.lokib200_step_injected(self.h, n, e.ctypes.data_as(C.c_void_p), float(nu_trial), _dp(ts), _dp(d), d.shape[1],
+                                                  out.ctypes.data_as(C.c_void_p), ev.ctypes.data_as(C.c_void_p)))
+        return out, ev
+
+    # --- histograms ---
+    def set_histogram_grid(self, max_eedf_energy):
+        self._check(self.L.lokib200_set_histogram_grid(self.h, float(max_eedf_energy)))
+
+    def sample_histograms(self, phase_index=-1):
+        self._check(self.L.lokib200_sample_histograms(self.h, int(phase_index)))
+
+    def fetch_histograms(self, periodic=False):
+        c = self.cfg
+        eeh = np.zeros(c.n_energy_cells); eah = np.zeros((c.n_energy_cells, c.n_cos_cells)); evh = np.zeros((c.n_radial_cells, c.n_axial_cells))
+        per = np.zeros((c.n_phases, c.n_energy_cells)) if periodic else None
+        self._check(self.L.lokib200_fetch_histograms(self.h, _dp(eeh), _dp(eah), _dp(evh), _dp(per) if periodic else None))
+        return (eeh, eah, evh, per) if periodic else (eeh, eah, evh)
+
+    # --- scalar helpers ---
+    def max_accel_energy(self, e0, dt):
+        return self.L.lokib200_max_accel_energy(self.h, float(e0), float(dt))
+
+    def check_nu_trial(self, max_energy, nu_trial, horizon=10.0):
+        nu = C.c_double(float(nu_trial))
+        self._check(self.L.lokib200_check_nu_trial(self.h, float(max_energy), float(horizon), self.energy_max_elastic, C.byref(nu)))
+        return nu.value
+
+    def launch_count(self):
+        return int(self.L.lokib200_launch_count(self.h))
+
+    def kernel_time_ms(self):
+        ms = C.c_double(); n = C.c_int64()
+        self._check(self.L.lokib200_kernel_time_ms(self.h, C.byref(ms), C.byref(n)))
+        return ms.value, n.value

@@ -1,0 +1,445 @@
+// lk_kernels.cuh -- sm_100a kernels of the electron Monte Carlo hot path.
+//
+//   k_init_ensemble   K0  initial Maxwellian                         (BMC.C:491-508)
+//   k_advance         K1  advance every electron to t_sync           (BMC.C:617-688, 804-1280) + tallies of BMC.C:1293-1339
+//                         (+ fused ensemble sums / histograms when no birth/death channel exists)
+//   k_pc_*            K2  birth/death population control at t_sync   (BMC.C:1341-1407, batched)
+//   k_sample          K3  ensemble sums + histograms as a separate pass (BMC.C:1410-1454, 1551-1571)
+//   k_finalize            fixed-order reduction of the per-block partials into the result vector
+//   k_step_injected       parity entry: one loop-body pass per thread with host-supplied draws
+//
+// One electron per thread; a warp stays converged at the end of every event round so that tallies use full-mask warp
+// primitives.  Per-block partial results are combined in a fixed order (k_finalize) so that all integer-valued outputs and
+// the ensemble sums are reproducible run to run.
+#pragma once
+#include "lk_physics.cuh"
+
+namespace lk {
+
+constexpr int ADV_THREADS = 256;
+constexpr int ADV_WARPS = ADV_THREADS / 32;
+constexpr int CHILD_STACK = 4;          // pending ejected electrons per thread inside one interval
+constexpr unsigned FULL = 0xFFFFFFFFu;
+
+// result vector layout: mirrors the LOKIB200_R_* enum of include/lokib200.h (static_asserted in lokib200.cu)
+enum : int {
+  R_N_REAL = 0, R_N_NULL = 1, R_N_BORN = 2, R_N_ATTACHED = 3, R_GAIN_FIELD = 4, R_GROWTH = 5, R_SUM_EPS = 6, R_SUM_R = 7, R_SUM_V = 10,
+  R_SUM_RR = 13, R_SUM_RV = 22, R_N_SAMPLED = 31, R_N_TABLE_CLAMPED = 32, R_N_NU_EXCEEDED = 33, R_SUM_COUNT = 34, R_MAX_EPS = 34,
+  R_MAX_EPS_SEEN = 35, R_HEADER = 36
+};
+constexpr int N_SAMPLE_SUMS = 26;        // R_SUM_EPS .. R_N_SAMPLED
+
+struct State { double *x, *y, *z, *vx, *vy, *vz, *tcf, *nue; };
+
+enum : int { C_BIRTHS = 0, C_DEAD = 1, C_FREED = 2, C_PLACED = 3, C_OVERFLOW = 4, C_TERMS = 5, C_COUNT = 8 };
+
+struct Lists {
+  double* birth;              // [8][birth_cap]: x y z vx vy vz tcf nue of electrons born inside the interval, already at t_sync
+  unsigned int* dead;         // [dead_cap] slots whose electron attached
+  unsigned int* freed;        // [birth_cap] slots vacated by the surplus lottery
+  unsigned int* claim;        // [n + birth_cap] lottery claims (0 = free)
+  unsigned char* dead_flag;   // [n]
+  double* growth_terms;       // [birth_cap + dead_cap] signed energyGrowth contributions
+  unsigned int* counters;     // [C_COUNT]
+  unsigned int birth_cap, dead_cap;
+};
+
+struct HistGrid {             // grids of BMC.C:1862-1883; steps computed on the host exactly as Eigen::LinSpaced does
+  int enabled, cylindrical, nEn, nC, nR, nA, phase, pad;
+  double e_step, c_first, c_step, r_step, a_first, a_step;
+  unsigned long long *eeh, *eah, *evh, *eeh_phase;   // eeh_phase already points at the row of the current phase (or null)
+};
+
+struct AdvArgs {
+  long long n;
+  unsigned long long first_id, seed;
+  unsigned int interval, pad;
+  double nu_trial, t0, t_sync;
+};
+
+// ------------------------------------------------------------------ sampling helpers ------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(FULL, v, o));
+  return v;
+}
+
+// ensemble sums of calculateMeanDataForSwarmParams (BMC.C:1432-1444) for one warp of electrons -> per-warp accumulators
+__device__ __forceinline__ void sample_moments(bool alive, double x, double y, double z, double vx, double vy, double vz, double eps, double* warp_acc, int lane) {
+  double val[N_SAMPLE_SUMS];
+  const double a = alive ? 1.0 : 0.0;
+  if (!alive) { x = y = z = vx = vy = vz = eps = 0.0; }
+  val[0] = eps;
+  val[1] = x; val[2] = y; val[3] = z;
+  val[4] = vx; val[5] = vy; val[6] = vz;
+  val[7] = x * x; val[8] = x * y; val[9] = x * z;
+  val[10] = val[8]; val[11] = y * y; val[12] = y * z;
+  val[13] = val[9]; val[14] = val[12]; val[15] = z * z;
+  val[16] = x * vx; val[17] = x * vy; val[18] = x * vz;
+  val[19] = y * vx; val[20] = y * vy; val[21] = y * vz;
+  val[22] = z * vx; val[23] = z * vy; val[24] = z * vz;
+  val[25] = a;
+#pragma unroll
+  for (int j = 0; j < N_SAMPLE_SUMS; ++j) {
+    if (j == 10 || j == 13 || j == 14) continue;   // symmetric entries of r r^T are filled in by k_finalize
+    const double s = warp_sum(val[j]);
+    if (lane == 0) warp_acc[R_SUM_EPS + j] += s;
+  }
+}
+
+// histogramCount / histogram2DCount (Math.C:61-81, :106-127) for one electron
+__device__ __forceinline__ void sample_histograms(const HistGrid& h, double vx, double vy, double vz, double eps, unsigned int* s_eeh) {
+  const int ie = static_cast<int>((eps - 0.0) / h.e_step);
+  if (ie < h.nEn) atomicAdd(&s_eeh[ie], 1u);
+  if (h.cylindrical) {
+    const double cosang = vz / sqrt((vx * vx + vy * vy) + vz * vz);
+    const int ic = static_cast<int>((cosang - h.c_first) / h.c_step);
+    if (ie < h.nEn && ie >= 0 && ic < h.nC && ic >= 0) atomicAdd(&h.eah[static_cast<size_t>(ie) * h.nC + ic], 1ull);
+    const double vr = sqrt(vx * vx + vy * vy);
+    const int ir = static_cast<int>((vr - 0.0) / h.r_step), ia = static_cast<int>((vz - h.a_first) / h.a_step);
+    if (ir < h.nR && ir >= 0 && ia < h.nA && ia >= 0) atomicAdd(&h.evh[static_cast<size_t>(ir) * h.nA + ia], 1ull);
+  }
+}
+
+__device__ __forceinline__ void flush_energy_histogram(const HistGrid& h, const unsigned int* s_eeh) {
+  for (int b = threadIdx.x; b < h.nEn; b += blockDim.x) {
+    const unsigned int c = s_eeh[b];
+    if (c) {
+      atomicAdd(&h.eeh[b], static_cast<unsigned long long>(c));
+      if (h.eeh_phase) atomicAdd(&h.eeh_phase[b], static_cast<unsigned long long>(c));
+    }
+  }
+}
+
+// per-block partials -> global, in a fixed layout [block][R_HEADER + 3P]
+__device__ __forceinline__ void write_partials(double (*s_acc)[R_HEADER], const unsigned int* s_cnt, const double* s_gain, const double* s_loss,
+                                               int P, double* partials) {
+  const int len = R_HEADER + 3 * P;
+  double* out = partials + static_cast<size_t>(blockIdx.x) * len;
+  for (int j = threadIdx.x; j < R_HEADER; j += blockDim.x) {
+    double v = s_acc[0][j];
+    for (int w = 1; w < ADV_WARPS; ++w) v = (j >= R_SUM_COUNT) ? fmax(v, s_acc[w][j]) : v + s_acc[w][j];
+    out[j] = v;
+  }
+  for (int k = threadIdx.x; k < P; k += blockDim.x) {
+    out[R_HEADER + k] = s_cnt ? static_cast<double>(s_cnt[k]) : 0.0;
+    out[R_HEADER + P + k] = s_gain ? s_gain[k] : 0.0;
+    out[R_HEADER + 2 * P + k] = s_loss ? s_loss[k] : 0.0;
+  }
+}
+
+// ------------------------------------------------------------------ K0 ------------------------------------------------------------------
+// evaluateNonConstantVariables, ensemble part (BMC.C:491-508): r = 0, v ~ Maxwellian(sd) via unitNormalRand3 (Math.C:54-59), t_cf undefined
+__global__ void __launch_bounds__(256) k_init_ensemble(State s, long long n, unsigned long long first_id, unsigned long long seed, double sd,
+                                                        unsigned long long* max_eps_bits) {
+  double mx = 0;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    PhiloxRng rng; rng.init(seed, first_id + static_cast<unsigned long long>(i), INIT_INTERVAL);
+    const double r1 = rng.next(), r2 = rng.next(), r3 = rng.next(), r4 = rng.next();
+    const double a1 = sqrt(-2.0 * log(r1)), a2 = 2.0 * PI * r2;
+    const double vx = a1 * cos(a2) * sd, vy = a1 * sin(a2) * sd, vz = sqrt(-2.0 * log(r3)) * cos(2.0 * PI * r4) * sd;
+    s.x[i] = 0; s.y[i] = 0; s.z[i] = 0; s.vx[i] = vx; s.vy[i] = vy; s.vz[i] = vz; s.tcf[i] = NON_DEF; s.nue[i] = 0;
+    mx = fmax(mx, kinetic_eV(vx, vy, vz));
+  }
+  mx = warp_max(mx);
+  if ((threadIdx.x & 31) == 0) atomicMax(max_eps_bits, static_cast<unsigned long long>(__double_as_longlong(mx)));   // eps >= 0: bit order == value order
+}
+
+// ------------------------------------------------------------------ K1 ------------------------------------------------------------------
+template <int FIELD, int GT, bool SAMPLE>
+__global__ void __launch_bounds__(ADV_THREADS, 2) k_advance(const Model m, const State s, const Lists L, const AdvArgs a, const HistGrid h,
+                                                             double* __restrict__ partials) {
+  extern __shared__ unsigned char smem_raw[];
+  // dynamic smem: gain[P] | loss[P] | cnt[P] | eeh[nEn]
+  double* s_gain = reinterpret_cast<double*>(smem_raw);
+  double* s_loss = s_gain + m.P;
+  unsigned int* s_cnt = reinterpret_cast<unsigned int*>(s_loss + m.P);
+  unsigned int* s_eeh = s_cnt + m.P;
+  __shared__ double s_acc[ADV_WARPS][R_HEADER];
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int k = threadIdx.x; k < m.P; k += blockDim.x) { s_gain[k] = 0; s_loss[k] = 0; s_cnt[k] = 0; }
+  if (SAMPLE && h.enabled) for (int b = threadIdx.x; b < h.nEn; b += blockDim.x) s_eeh[b] = 0;
+  for (int j = threadIdx.x; j < ADV_WARPS * R_HEADER; j += blockDim.x) (&s_acc[0][0])[j] = 0;
+  __syncthreads();
+
+  unsigned int n_real = 0, n_null = 0, n_born = 0, n_att = 0, n_clamp = 0, n_nuex = 0;
+  double gain_field = 0, max_end = 0, max_seen = 0;
+  double stk[CHILD_STACK][7];
+
+  const long long n_round = (a.n + 31) & ~31ll;
+  for (long long i = blockIdx.x * static_cast<long long>(ADV_THREADS) + threadIdx.x; i < n_round; i += static_cast<long long>(gridDim.x) * ADV_THREADS) {
+    bool active = i < a.n;
+    Particle p = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    PhiloxRng rng;
+    rng.init(a.seed, 0, a.interval);
+    if (active) {
+      p.x = s.x[i]; p.y = s.y[i]; p.z = s.z[i]; p.vx = s.vx[i]; p.vy = s.vy[i]; p.vz = s.vz[i]; p.tcf = s.tcf[i]; p.nue = s.nue[i];
+      p.t = a.t0; p.eps = kinetic_eV(p.vx, p.vy, p.vz);
+      rng.init(a.seed, a.first_id + static_cast<unsigned long long>(i), a.interval);
+    }
+    bool is_child = false, alive = false;
+    int sp = 0;
+    Particle f = p;   // state of the slot's electron at t_sync (stored coalesced after the loop)
+
+    while (__any_sync(FULL, active)) {
+      int chosen = NOT_ADVANCED;
+      double dE = 0;
+      if (active) {
+        EventOut o; o.table_clamped = 0; o.nu_exceeded = 0; o.dE = 0;
+        chosen = event<FIELD, GT>(m, p, a.nu_trial, a.t_sync, rng, o);
+        gain_field += o.gain_field;
+        max_seen = fmax(max_seen, p.eps);
+        n_clamp += o.table_clamped; n_nuex += o.nu_exceeded;
+        bool done = false;
+        if (chosen == PARTIAL_FLIGHT) {
+          if (!is_child) { f = p; alive = true; max_end = fmax(max_end, p.eps); }
+          else {
+            const unsigned int idx = atomicAdd(&L.counters[C_BIRTHS], 1u);
+            if (idx < L.birth_cap) {
+              double* b = L.birth + idx; const size_t c = L.birth_cap;
+              b[0] = p.x; b[c] = p.y; b[2 * c] = p.z; b[3 * c] = p.vx; b[4 * c] = p.vy; b[5 * c] = p.vz; b[6 * c] = p.tcf; b[7 * c] = p.nue;
+            } else atomicExch(&L.counters[C_OVERFLOW], 1u);
+          }
+          done = true;
+        } else if (chosen >= 0) {
+          dE = o.dE;
+          const int type = __ldg(&m.type[chosen]);
+          if (type == T_IONIZATION) {                                // the ejected electron waits on the thread's stack (BMC.C:1346-1353 semantics:
+            ++n_born;                                                 // parent's clock, undefined free time)
+            if (sp < CHILD_STACK) {
+              stk[sp][0] = o.ejx; stk[sp][1] = o.ejy; stk[sp][2] = o.ejz; stk[sp][3] = o.ejvx; stk[sp][4] = o.ejvy; stk[sp][5] = o.ejvz; stk[sp][6] = p.t;
+              ++sp;
+            } else atomicExch(&L.counters[C_OVERFLOW], 1u);
+          } else if (type == T_ATTACHMENT) {
+            ++n_att;
+            if (!is_child) {
+              const unsigned int idx = atomicAdd(&L.counters[C_DEAD], 1u);
+              if (idx < L.dead_cap) { L.dead[idx] = static_cast<unsigned int>(i); L.dead_flag[i] = 1; } else atomicExch(&L.counters[C_OVERFLOW], 1u);
+            }
+            done = true;
+          }
+        }
+        if (done) {
+          if (sp > 0) {
+            --sp;
+            p.x = stk[sp][0]; p.y = stk[sp][1]; p.z = stk[sp][2]; p.vx = stk[sp][3]; p.vy = stk[sp][4]; p.vz = stk[sp][5]; p.t = stk[sp][6];
+            p.eps = kinetic_eV(p.vx, p.vy, p.vz); p.tcf = NON_DEF; p.nue = a.nu_trial;
+            is_child = true;
+          } else active = false;
+        }
+      }
+      // ---- converged: tallies of nonParallelCollisionTasks (BMC.C:1303-1328) ----
+      const bool real = chosen >= 0;
+      n_real += real ? 1u : 0u;
+      n_null += (chosen == NULL_COLLISION) ? 1u : 0u;
+      const unsigned rm = __ballot_sync(FULL, real);
+      if (real) {
+        const unsigned peers = __match_any_sync(rm, chosen);
+        const double g = (dE >= 0) ? dE : 0.0, l = (dE >= 0) ? 0.0 : dE;
+        double gs = 0, ls = 0;
+        for (unsigned rem = peers; rem; rem &= rem - 1) {
+          const int src = __ffs(rem) - 1;
+          gs += __shfl_sync(peers, g, src); ls += __shfl_sync(peers, l, src);
+        }
+        if (lane == __ffs(peers) - 1) {
+          atomicAdd(&s_cnt[chosen], static_cast<unsigned int>(__popc(peers)));
+          if (gs != 0) atomicAdd(&s_gain[chosen], gs);
+          if (ls != 0) atomicAdd(&s_loss[chosen], ls);
+        }
+      }
+    }
+
+    if (alive) {   // coalesced write-back of the 8 state words
+      s.x[i] = f.x; s.y[i] = f.y; s.z[i] = f.z; s.vx[i] = f.vx; s.vy[i] = f.vy; s.vz[i] = f.vz; s.tcf[i] = f.tcf; s.nue[i] = f.nue;
+    }
+    if (SAMPLE) {
+      sample_moments(alive, f.x, f.y, f.z, f.vx, f.vy, f.vz, f.eps, s_acc[warp], lane);
+      if (h.enabled && alive) sample_histograms(h, f.vx, f.vy, f.vz, f.eps, s_eeh);
+    }
+  }
+
+  // thread tallies -> warp -> block partials
+  {
+    const double v0 = warp_sum(static_cast<double>(n_real)), v1 = warp_sum(static_cast<double>(n_null)), v2 = warp_sum(static_cast<double>(n_born)),
+                 v3 = warp_sum(static_cast<double>(n_att)), v4 = warp_sum(gain_field), v5 = warp_sum(static_cast<double>(n_clamp)),
+                 v6 = warp_sum(static_cast<double>(n_nuex)), m0 = warp_max(max_end), m1 = warp_max(max_seen);
+    if (lane == 0) {
+      double* acc = s_acc[warp];
+      acc[R_N_REAL] += v0; acc[R_N_NULL] += v1; acc[R_N_BORN] += v2; acc[R_N_ATTACHED] += v3; acc[R_GAIN_FIELD] += v4;
+      acc[R_N_TABLE_CLAMPED] += v5; acc[R_N_NU_EXCEEDED] += v6; acc[R_MAX_EPS] = m0; acc[R_MAX_EPS_SEEN] = m1;
+    }
+  }
+  __syncthreads();
+  write_partials(s_acc, s_cnt, s_gain, s_loss, m.P, partials);
+  if (SAMPLE && h.enabled) flush_energy_histogram(h, s_eeh);
+}
+
+// ------------------------------------------------------------------ K3 ------------------------------------------------------------------
+// ensemble sums + histograms as a separate pass (used when births/deaths can change the ensemble at t_sync)
+__global__ void __launch_bounds__(ADV_THREADS) k_sample(const State s, long long n, const HistGrid h, int P, double* __restrict__ partials) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned int* s_eeh = reinterpret_cast<unsigned int*>(smem_raw);
+  __shared__ double s_acc[ADV_WARPS][R_HEADER];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (h.enabled) for (int b = threadIdx.x; b < h.nEn; b += blockDim.x) s_eeh[b] = 0;
+  for (int j = threadIdx.x; j < ADV_WARPS * R_HEADER; j += blockDim.x) (&s_acc[0][0])[j] = 0;
+  __syncthreads();
+  double max_end = 0;
+  const long long n_round = (n + 31) & ~31ll;
+  for (long long i = blockIdx.x * static_cast<long long>(ADV_THREADS) + threadIdx.x; i < n_round; i += static_cast<long long>(gridDim.x) * ADV_THREADS) {
+    const bool alive = i < n;
+    double x = 0, y = 0, z = 0, vx = 0, vy = 0, vz = 0;
+    if (alive) { x = s.x[i]; y = s.y[i]; z = s.z[i]; vx = s.vx[i]; vy = s.vy[i]; vz = s.vz[i]; }
+    const double eps = kinetic_eV(vx, vy, vz);
+    max_end = fmax(max_end, eps);
+    sample_moments(alive, x, y, z, vx, vy, vz, eps, s_acc[warp], lane);
+    if (h.enabled && alive) sample_histograms(h, vx, vy, vz, eps, s_eeh);
+  }
+  const double m0 = warp_max(max_end);
+  if (lane == 0) s_acc[warp][R_MAX_EPS] = m0;
+  __syncthreads();
+  write_partials(s_acc, nullptr, nullptr, nullptr, P, partials);
+  if (h.enabled) flush_energy_histogram(h, s_eeh);
+}
+
+// ------------------------------------------------------------------ K2: population control ------------------------------------------------------------------
+// Batched form of BMC.C:1341-1407 applied once at t_sync (every electron carries the same clock there):
+//   (a) attached slots are refilled by ejected electrons, last born first (:1346-1359);
+//   (b) attached slots left over get a copy of a uniformly drawn non-attached electron (:1361-1376);
+//   (c) K surplus ejected electrons: a uniformly random K-subset of the (n + K) pool is removed, exactly the distribution the
+//       reference's sequential draw-and-replace loop produces (:1380-1407); survivors move into the vacated slots.
+__device__ __forceinline__ void copy_birth_to_slot(const State& s, const Lists& L, unsigned int slot, unsigned int b) {
+  const double* src = L.birth + b; const size_t c = L.birth_cap;
+  s.x[slot] = src[0]; s.y[slot] = src[c]; s.z[slot] = src[2 * c]; s.vx[slot] = src[3 * c]; s.vy[slot] = src[4 * c]; s.vz[slot] = src[5 * c];
+  s.tcf[slot] = src[6 * c]; s.nue[slot] = src[7 * c];
+}
+
+__global__ void k_pc_fill(const State s, const Lists L) {
+  const unsigned int nB = min(L.counters[C_BIRTHS], L.birth_cap), nD = min(L.counters[C_DEAD], L.dead_cap), nF = min(nB, nD);
+  for (unsigned int j = blockIdx.x * blockDim.x + threadIdx.x; j < nF; j += gridDim.x * blockDim.x) {
+    const unsigned int slot = L.dead[j];
+    copy_birth_to_slot(s, L, slot, nB - 1 - j);
+    L.dead_flag[slot] = 0;
+  }
+}
+
+__global__ void k_pc_copy(const State s, const Lists L, long long n, unsigned long long first_id, unsigned long long seed, unsigned int interval) {
+  const unsigned int nB = min(L.counters[C_BIRTHS], L.birth_cap), nD = min(L.counters[C_DEAD], L.dead_cap);
+  for (unsigned int j = nB + blockIdx.x * blockDim.x + threadIdx.x; j < nD; j += gridDim.x * blockDim.x) {
+    const unsigned int slot = L.dead[j];
+    PhiloxRng rng; rng.init(seed, first_id + slot, interval, 0); rng.c2 = interval; rng.c1 |= POPCTRL_INTERVAL_BIT;
+    long long donor = 0;
+    for (int it = 0; it < 4096; ++it) {                                   // BMC.C:1362-1365
+      donor = static_cast<long long>(fmin(rng.next() * static_cast<double>(n), static_cast<double>(n - 1)));
+      if (!L.dead_flag[donor]) break;
+    }
+    const double vx = s.vx[donor], vy = s.vy[donor], vz = s.vz[donor];
+    L.growth_terms[atomicAdd(&L.counters[C_TERMS], 1u)] = kinetic_eV(vx, vy, vz);   // energyGrowth += eps_donor (:1367)
+    s.x[slot] = s.x[donor]; s.y[slot] = s.y[donor]; s.z[slot] = s.z[donor]; s.vx[slot] = vx; s.vy[slot] = vy; s.vz[slot] = vz;
+    s.tcf[slot] = s.tcf[donor]; s.nue[slot] = s.nue[donor];               // copies inherit t_cf and nu_e (:1373-1374)
+  }
+}
+
+__global__ void k_pc_lottery(const State s, const Lists L, long long n, unsigned long long first_id, unsigned long long seed, unsigned int interval) {
+  const unsigned int nB = min(L.counters[C_BIRTHS], L.birth_cap), nD = min(L.counters[C_DEAD], L.dead_cap);
+  if (nB <= nD) return;
+  const unsigned int K = nB - nD;
+  const double pool = static_cast<double>(n) + static_cast<double>(K);
+  for (unsigned int b = blockIdx.x * blockDim.x + threadIdx.x; b < K; b += gridDim.x * blockDim.x) {
+    PhiloxRng rng; rng.init(seed, first_id + static_cast<unsigned long long>(n) + b, interval, 0); rng.c1 |= POPCTRL_INTERVAL_BIT;
+    long long j = 0;
+    for (int it = 0; it < 1 << 20; ++it) {                                // sampling without replacement by rejection
+      j = static_cast<long long>(fmin(rng.next() * pool, pool - 1.0));
+      if (atomicCAS(&L.claim[j], 0u, 1u) == 0u) break;
+    }
+    double eps;
+    if (j < n) {                                                          // a member of the ensemble leaves (:1384-1395)
+      L.freed[atomicAdd(&L.counters[C_FREED], 1u)] = static_cast<unsigned int>(j);
+      eps = kinetic_eV(s.vx[j], s.vy[j], s.vz[j]);
+    } else {                                                              // an ejected electron is dropped (:1397-1403)
+      const size_t c = L.birth_cap; const double* src = L.birth + (j - n);
+      eps = kinetic_eV(src[3 * c], src[4 * c], src[5 * c]);
+    }
+    L.growth_terms[atomicAdd(&L.counters[C_TERMS], 1u)] = -eps;
+  }
+}
+
+__global__ void k_pc_place(const State s, const Lists L, long long n) {
+  const unsigned int nB = min(L.counters[C_BIRTHS], L.birth_cap), nD = min(L.counters[C_DEAD], L.dead_cap);
+  if (nB <= nD) return;
+  const unsigned int K = nB - nD;
+  for (unsigned int b = blockIdx.x * blockDim.x + threadIdx.x; b < K; b += gridDim.x * blockDim.x) {
+    if (L.claim[n + b] == 0u) copy_birth_to_slot(s, L, L.freed[atomicAdd(&L.counters[C_PLACED], 1u)], b);
+  }
+}
+
+// sums the growth terms in a fixed order into pc_result[0], clears claims / flags / counters for the next interval
+__global__ void k_pc_reset(const Lists L, long long n, double* pc_result) {
+  const unsigned int nB = min(L.counters[C_BIRTHS], L.birth_cap), nD = min(L.counters[C_DEAD], L.dead_cap);
+  const unsigned int K = (nB > nD) ? nB - nD : 0u, nFreed = L.counters[C_FREED], nTerms = L.counters[C_TERMS];
+  for (unsigned int b = threadIdx.x; b < K; b += blockDim.x) L.claim[n + b] = 0u;
+  for (unsigned int f = threadIdx.x; f < nFreed; f += blockDim.x) L.claim[L.freed[f]] = 0u;
+  for (unsigned int j = threadIdx.x; j < nD; j += blockDim.x) L.dead_flag[L.dead[j]] = 0;
+  __shared__ double red[256];
+  double acc = 0;
+  for (unsigned int t = threadIdx.x; t < nTerms; t += blockDim.x) acc += L.growth_terms[t];
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double tot = 0;
+    for (int t = 0; t < 256; ++t) tot += red[t];
+    pc_result[0] = tot;
+    pc_result[1] = static_cast<double>(L.counters[C_OVERFLOW]);
+  }
+  __syncthreads();
+  if (threadIdx.x < C_COUNT) L.counters[threadIdx.x] = 0u;
+}
+
+// ------------------------------------------------------------------ finalize ------------------------------------------------------------------
+// result[j] = fixed-order combination over blocks of the K1 partials (+ K3 partials for the sampled sums, + K2 growth)
+__global__ void k_finalize(const double* __restrict__ adv_partials, int adv_blocks, const double* __restrict__ smp_partials, int smp_blocks,
+                           const double* __restrict__ pc_result, int P, double* __restrict__ result) {
+  const int len = R_HEADER + 3 * P;
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < len; j += gridDim.x * blockDim.x) {
+    int src = j;   // symmetric entries of sum r r^T are accumulated once (xy, xz, yz) and mirrored here
+    if (j == R_SUM_RR + 3) src = R_SUM_RR + 1; else if (j == R_SUM_RR + 6) src = R_SUM_RR + 2; else if (j == R_SUM_RR + 7) src = R_SUM_RR + 5;
+    const bool is_max = (j >= R_SUM_COUNT && j < R_HEADER);
+    const bool from_sample = smp_partials && ((j >= R_SUM_EPS && j <= R_N_SAMPLED) || j == R_MAX_EPS);
+    const double* part = from_sample ? smp_partials : adv_partials;
+    const int nb = from_sample ? smp_blocks : adv_blocks;
+    double v = 0;
+    for (int b = 0; b < nb; ++b) { const double t = part[static_cast<size_t>(b) * len + src]; v = is_max ? fmax(v, t) : v + t; }
+    if (j == R_GROWTH && pc_result) v = pc_result[0];
+    result[j] = v;
+  }
+}
+
+// ------------------------------------------------------------------ parity entry ------------------------------------------------------------------
+struct ElectronIO { double r[3], v[3], energy, t, t_cf, nu_e; };
+struct EventIO { int chosen, draws_used; double dE, dE_rel, gain_field, ej_r[3], ej_v[3], ej_energy; };
+
+template <int FIELD, int GT>
+__global__ void k_step_injected(const Model m, int n, const ElectronIO* __restrict__ in, double nu_trial, const double* __restrict__ t_sync,
+                                const double* __restrict__ draws, int n_draws, ElectronIO* __restrict__ out, EventIO* __restrict__ ev) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Particle p;
+  p.x = in[i].r[0]; p.y = in[i].r[1]; p.z = in[i].r[2]; p.vx = in[i].v[0]; p.vy = in[i].v[1]; p.vz = in[i].v[2];
+  p.eps = in[i].energy; p.t = in[i].t; p.tcf = in[i].t_cf; p.nue = in[i].nu_e;
+  InjectedRng rng{draws + static_cast<size_t>(i) * n_draws, n_draws, 0};
+  EventOut o; o.dE = 0; o.dE_rel = 0; o.gain_field = 0; o.ejx = o.ejy = o.ejz = o.ejvx = o.ejvy = o.ejvz = o.ejeps = 0; o.table_clamped = 0; o.nu_exceeded = 0;
+  const int chosen = event<FIELD, GT>(m, p, nu_trial, t_sync[i], rng, o);
+  out[i].r[0] = p.x; out[i].r[1] = p.y; out[i].r[2] = p.z; out[i].v[0] = p.vx; out[i].v[1] = p.vy; out[i].v[2] = p.vz;
+  out[i].energy = p.eps; out[i].t = p.t; out[i].t_cf = p.tcf; out[i].nu_e = p.nue;
+  ev[i].chosen = chosen; ev[i].draws_used = rng.used; ev[i].dE = o.dE; ev[i].dE_rel = o.dE_rel; ev[i].gain_field = o.gain_field;
+  ev[i].ej_r[0] = o.ejx; ev[i].ej_r[1] = o.ejy; ev[i].ej_r[2] = o.ejz; ev[i].ej_v[0] = o.ejvx; ev[i].ej_v[1] = o.ejvy; ev[i].ej_v[2] = o.ejvz;
+  ev[i].ej_energy = o.ejeps;
+}
+
+}  // namespace lk

@@ -162,9 +162,9 @@ void lo_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out
   out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
-static inline double u53(uint32_t hi, uint32_t lo) {   /* (k + 0.5) 2^-53, k = top 53 bits: strictly inside (0,1) */
-  const uint64_t k = (((uint64_t)hi << 32) | lo) >> 11;
-  return ((double)k + 0.5) * (1.0 / 9007199254740992.0);
+static inline double u53(uint32_t hi, uint32_t lo) {   /* (k + 0.5) 2^-52, k = top 52 bits (k + 0.5 is exact in a double): strictly inside (0,1) */
+  const uint64_t k = (((uint64_t)hi << 32) | lo) >> 12;
+  return ((double)k + 0.5) * (1.0 / 4503599627370496.0);
 }
 
 /* counter = (id_lo, id_hi, interval, j/2), key = (seed_lo, seed_hi): two uniforms per Philox call */

@@ -1,0 +1,268 @@
+"""GPU parity tests: the CUDA path (through the C ABI, include/lokib200.h) against
+  (1) golden vectors produced by the unmodified reference (tests/golden, oracle/gen_golden.py), and
+  (2) the CPU oracle (oracle/lokioracle.c, itself pinned to the same golden vectors by test_oracle_golden.py).
+
+Tolerance for floating point: 1e-12 relative (BASELINE.json:north_star), measured against the natural scale of each quantity
+(vector norms for r and v; the electron energy for energy changes, which are differences of two energies).
+Integer-valued outputs (chosen process, draws consumed, event counters, histogram counts) must be bit-exact.
+"""
+import numpy as np
+import pytest
+
+import golden_io as gio
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-12
+
+
+def _engine(g, n, **kw):
+    import loki_mc_b200 as lk
+    return lk.Engine(g, n, **kw)
+
+
+def _oracle():
+    from oracle import lokioracle as lo
+    return lo
+
+
+@pytest.fixture(scope="module", params=gio.MODELS)
+def gm(request):
+    return gio.load(request.param)
+
+
+def rel_vec(a, b, floor=0.0):
+    a = np.asarray(a, float); b = np.asarray(b, float)
+    return np.linalg.norm(a - b, axis=-1) / np.maximum(np.linalg.norm(b, axis=-1), floor)
+
+
+def test_tables_bit_exact(gm):
+    g = gm
+    eng = _engine(g, 256)
+    eng.build_tables(float(g["tab_maxE"]))
+    info = eng.table_info()
+    assert info["nE"] == int(g["tab_nE"]) and info["dE"] == float(g["tab_dE"])
+    cum, nu_tot, nu_max = eng.get_tables()
+    rows = g["tab_rows"]
+    assert np.array_equal(cum[rows], g["tab_cum_rows"])
+    assert np.array_equal(nu_tot, g["tab_nu_tot"])
+    assert np.array_equal(nu_max, g["tab_nu_max"])
+    lo = _oracle()
+    t = lo.Model(g).build_tables(float(g["tab_maxE"]))
+    assert np.array_equal(cum, t["cum"])
+    for (e0, dt), want in zip(g["maxaccel_in"], g["maxaccel_out"]):
+        assert abs(eng.max_accel_energy(e0, dt) - want) <= 1e-14 * abs(want)
+    eng.close()
+
+
+def test_step_injected_matches_reference(gm):
+    """every golden event of the reference, replayed on the GPU with the same injected draws"""
+    from loki_mc_b200._capi import ELECTRON_DTYPE
+    g = gm
+    eng = _engine(g, 256)
+    eng.build_tables(float(g["tab_maxE"]))
+    I, O = gio.EV_IN, gio.EV_OUT
+    ein, eout = g["ev_in"], g["ev_out"]
+    n = len(ein)
+    el = np.zeros(n, dtype=ELECTRON_DTYPE)
+    el["r"] = ein[:, I["r"]]; el["v"] = ein[:, I["v"]]; el["energy"] = gio.energy_eV(ein[:, I["v"]])
+    el["t"] = ein[:, I["t_e"]]; el["t_cf"] = ein[:, I["t_cf"]]; el["nu_e"] = ein[:, I["nu_e"]]
+    nu_trial = float(ein[0, I["nu_trial"]])
+    assert np.all(ein[:, I["nu_trial"]] == nu_trial)
+    out, ev = eng.step_injected(el, nu_trial, ein[:, I["t_sync"]], ein[:, I["draws"]])
+    chosen_ref = eout[:, O["chosen"]].astype(int)
+    assert np.array_equal(ev["chosen"], chosen_ref)
+    assert np.array_equal(ev["draws_used"], eout[:, O["draws_used"]].astype(int))
+    vin = np.linalg.norm(ein[:, I["v"]], axis=1)
+    assert rel_vec(out["r"], eout[:, O["r"]]).max() <= RTOL
+    # velocity: relative to the larger of the outgoing and incoming speed (near-threshold collisions leave a slow electron)
+    assert (np.linalg.norm(out["v"] - eout[:, O["v"]], axis=1) / np.maximum(np.linalg.norm(eout[:, O["v"]], axis=1), vin)).max() <= RTOL
+    eps_scale = np.maximum(np.abs(eout[:, O["eps"]]), el["energy"])
+    assert (np.abs(out["energy"] - eout[:, O["eps"]]) / eps_scale).max() <= RTOL
+    assert (np.abs(out["t"] - eout[:, O["t_e"]]) <= RTOL * np.abs(eout[:, O["t_e"]]) + 1e-30).all()
+    assert (np.abs(out["t_cf"] - eout[:, O["t_cf"]]) <= RTOL * np.abs(eout[:, O["t_cf"]])).all()
+    assert np.array_equal(out["nu_e"], eout[:, O["nu_e"]])
+    assert (np.abs(ev["gain_field"] - eout[:, O["gain_field"]]) / eps_scale).max() <= RTOL
+    real = chosen_ref >= 0
+    assert real.sum() > 100
+    assert (np.abs(ev["dE"] - eout[:, O["dE"]])[real] / eps_scale[real]).max() <= RTOL
+    assert np.abs(ev["dE_rel"] - eout[:, O["dE_rel"]])[real].max() <= 1e-11
+    ion = real.copy(); ion[real] = g["p_type"][chosen_ref[real]] == 1
+    if ion.any():
+        assert rel_vec(ev["ej_r"][ion], eout[ion][:, O["ej_r"]]).max() <= RTOL
+        assert (np.linalg.norm(ev["ej_v"][ion] - eout[ion][:, O["ej_v"]], axis=1) / vin[ion]).max() <= RTOL
+        assert (np.abs(ev["ej_energy"][ion] - eout[ion, O["ej_eps"]]) / eps_scale[ion]).max() <= RTOL
+    eng.close()
+
+
+NO_PC_MODELS = ["reid_dc", "reid_ac", "reid_b", "reid_ecr", "reid_acb", "reid_true_aniso"]
+
+
+def _start_state(g, n, rng, e_lo, e_hi):
+    eps = np.exp(rng.uniform(np.log(e_lo), np.log(e_hi), n))
+    d = rng.normal(size=(3, n)); d /= np.linalg.norm(d, axis=0)
+    v = d * np.sqrt(2 * eps * gio.QE / gio.ME)
+    r = rng.normal(size=(3, n)) * 1e-3
+    return np.vstack([r, v, np.full((1, n), -123456789.0), np.zeros((1, n))])
+
+
+@pytest.mark.parametrize("name", NO_PC_MODELS + ["n2_aniso", "arhe_true", "air"])
+def test_interval_matches_oracle_per_electron(name):
+    """three synchronisation intervals of a 4096-electron ensemble with the shared counter-based draw streams:
+    every electron must follow the oracle's trajectory (energies kept below any ionization/attachment threshold so that the
+    ensemble is not re-populated)."""
+    lo = _oracle()
+    g = gio.load(name)
+    n = 4096
+    rng = np.random.default_rng(12345)
+    e_hi = 3.0 if name in NO_PC_MODELS else 0.6
+    maxE = 10.0 if name in NO_PC_MODELS else 8.0
+    s0 = _start_state(g, n, rng, 1e-3, e_hi)
+    seed, first_id = 0xC0FFEE, 777
+    m = lo.Model(g); t = m.build_tables(maxE)
+    nu_trial = float(t["nu_max"][-1])
+    ens = lo.Ensemble(m, n, seed, first_id); ens.set(s0)
+    eng = _engine(g, n, seed=seed, first_electron_id=first_id)
+    eng.build_tables(maxE); eng.set_ensemble(s0, 0.0)
+    tsync = 0.0
+    for it in range(1, 4):
+        tsync += 1.0 / nu_trial
+        ro = ens.advance(nu_trial, tsync, it, population_control=0)
+        rg = eng.advance(nu_trial, tsync, sample=True)
+        assert ro["n_born"] == 0 and ro["n_attached"] == 0
+        R = __import__("loki_mc_b200").R
+        assert int(rg[R.N_REAL]) == ro["n_real"] and int(rg[R.N_NULL]) == ro["n_null"]
+        assert np.array_equal(rg[R.HEADER:R.HEADER + eng.P].astype(np.uint64), ro["counts"])
+        so, sg = ens.get(), eng.get_ensemble()
+        assert rel_vec(sg[0:3].T, so[0:3].T).max() <= RTOL
+        assert rel_vec(sg[3:6].T, so[3:6].T).max() <= 1e-11   # a few collisions compound; still far below physical relevance
+        assert np.allclose(sg[6], so[6], rtol=1e-11, atol=0) and np.array_equal(sg[7], so[7])
+        escale = np.abs(gio.energy_eV(so[3:6].T)).sum()
+        assert abs(rg[R.GAIN_FIELD] - ro["field"]) <= 1e-11 * escale
+        assert np.allclose(rg[R.HEADER + eng.P:R.HEADER + 2 * eng.P], ro["gain"], rtol=1e-10, atol=1e-12 * escale)
+        assert np.allclose(rg[R.HEADER + 2 * eng.P:R.HEADER + 3 * eng.P], ro["loss"], rtol=1e-10, atol=1e-12 * escale)
+        # ensemble sums against the oracle's moments of the same state (BMC.C:1432-1446)
+        mom = lo.moments(so)
+        assert rg[R.N_SAMPLED] == n
+        assert abs(rg[R.SUM_EPS] / n - mom[0]) <= 1e-11 * mom[0]
+        assert abs(rg[R.MAX_EPS] - mom[1]) <= 1e-11 * mom[1]
+        mr = rg[R.SUM_R:R.SUM_R + 3] / n; mv = rg[R.SUM_V:R.SUM_V + 3] / n
+        assert np.allclose(mr, mom[2:5], rtol=1e-9, atol=1e-12 * np.abs(so[0:3]).max())
+        assert np.allclose(mv, mom[5:8], rtol=1e-9, atol=1e-12 * np.abs(so[3:6]).max())
+        cov = rg[R.SUM_RR:R.SUM_RR + 9].reshape(3, 3) / n - np.outer(mr, mr)
+        assert np.allclose(cov.ravel(), mom[8:17], rtol=1e-8, atol=1e-10 * np.abs(mom[8:17]).max())
+        cvr = rg[R.SUM_RV:R.SUM_RV + 9].reshape(3, 3) / n - np.outer(mr, mv)
+        assert np.allclose(cvr.ravel(), mom[17:26], rtol=1e-8, atol=1e-10 * np.abs(mom[17:26]).max())
+    eng.close()
+
+
+def test_histograms_match_reference(gm):
+    g = gm
+    ens = g["ens"]; n = ens.shape[1]
+    eng = _engine(g, n)
+    s = np.vstack([ens, np.zeros((2, n))])
+    eng.set_ensemble(s, 0.0)
+    hdr = g["hist_hdr"]
+    eng.set_histogram_grid(float(hdr[4]))
+    eng.sample_histograms(-1)
+    eeh, eah, evh = eng.fetch_histograms()
+    assert np.array_equal(eeh, g["eeh"])
+    if g["cond"]["is_cylindrically_symmetric"]:
+        ne, nc, nr, na = (int(x) for x in hdr[:4])
+        want_eah = np.zeros((ne, nc)); want_eah[tuple(g["eah_idx"].T)] = g["eah_val"]
+        want_evh = np.zeros((nr, na)); want_evh[tuple(g["evh_idx"].T)] = g["evh_val"]
+        assert np.array_equal(eah, want_eah) and np.array_equal(evh, want_evh)
+    else:
+        assert eah.sum() == 0 and evh.sum() == 0
+    # accumulation + phase rows
+    eng.sample_histograms(3)
+    eeh2, _, _, per = eng.fetch_histograms(periodic=True)
+    assert np.array_equal(eeh2, 2 * g["eeh"]) and np.array_equal(per[3], g["eeh"]) and per.sum() == g["eeh"].sum()
+    eng.close()
+
+
+def test_init_ensemble_matches_oracle():
+    lo = _oracle()
+    g = gio.load("o2_sdcs")
+    n = 10000
+    eng = _engine(g, n, seed=99, first_electron_id=5)
+    mx = eng.init_ensemble(0.01)
+    m = lo.Model(g); ens = lo.Ensemble(m, n, 99, 5); ens.init(0.01)
+    so, sg = ens.get(), eng.get_ensemble()
+    assert np.all(sg[0:3] == 0)
+    assert rel_vec(sg[3:6].T, so[3:6].T).max() <= RTOL
+    assert np.all(sg[6] == -123456789.0)
+    assert abs(mx - ens.max_energy()) <= 1e-12 * mx
+    eng.close()
+
+
+def test_determinism_and_shard_invariance():
+    """same seed -> bit-identical ensemble; an ensemble split over two engines (shards keyed by global electron id) reproduces
+    the single-engine trajectories exactly, and its summed counters equal the single-engine counters."""
+    import loki_mc_b200 as lk
+    R = lk.R
+    g = gio.load("reid_acb")
+    n = 20000
+    rng = np.random.default_rng(7)
+    s0 = _start_state(g, n, rng, 1e-2, 5.0)
+    runs = []
+    for shards in (1, 1, 2):
+        res = []
+        out = np.zeros((8, n))
+        for sh in range(shards):
+            lo_i, hi_i = sh * n // shards, (sh + 1) * n // shards
+            eng = _engine(g, hi_i - lo_i, seed=1234, first_electron_id=lo_i)
+            eng.build_tables(12.0)
+            nu = eng.table_info()["nu_max_last"]
+            eng.set_ensemble(s0[:, lo_i:hi_i], 0.0)
+            acc = None
+            for it in range(1, 6):
+                r = eng.advance(nu, it / nu, sample=True)
+                acc = r.copy() if acc is None else acc + r
+            out[:, lo_i:hi_i] = eng.get_ensemble()
+            res.append(acc)
+            eng.close()
+        runs.append((out, sum(res)))
+    assert np.array_equal(runs[0][0], runs[1][0]) and np.array_equal(runs[0][1][:R.N_SAMPLED + 1], runs[1][1][:R.N_SAMPLED + 1])
+    assert np.array_equal(runs[0][0], runs[2][0])
+    P = len(g["p_type"])
+    for j in (R.N_REAL, R.N_NULL):
+        assert runs[0][1][j] == runs[2][1][j]
+    assert np.array_equal(runs[0][1][R.HEADER:R.HEADER + P], runs[2][1][R.HEADER:R.HEADER + P])
+    assert np.allclose(runs[0][1][R.SUM_EPS:R.N_SAMPLED], runs[2][1][R.SUM_EPS:R.N_SAMPLED], rtol=1e-12, atol=0)
+
+
+@pytest.mark.parametrize("name,n", [("n2_aniso", 10_000_000), ("reid_dc", 10_000_000)])
+def test_full_size_energy_balance(name, n):
+    """BASELINE.json config size (1e7 electrons): size-independent identities of one interval --
+    events are conserved, every electron is sampled once, and the change of the ensemble energy equals
+    field gain + collisional gain + collisional loss + growth (the power balance the reference checks, BMC.C:1769-1785)."""
+    import loki_mc_b200 as lk
+    R = lk.R
+    g = gio.load(name)
+    eng = _engine(g, n, seed=42)
+    mean_e = 3.0 if name == "n2_aniso" else 0.3
+    Tg = g["cond"]["gas_temperature"]
+    ratio = mean_e / (1.5 * 1.38064852e-23 * Tg / 1.6021766208e-19)
+    mx = eng.init_ensemble(ratio)
+    eng.build_tables(2.0 * mx)
+    nu = eng.check_nu_trial(mx, eng.table_info()["nu_max_last"], horizon=11.0)
+    P = eng.P
+    r0 = eng.advance(nu, 1e-3 / nu, sample=True)       # a very short interval to get the starting sums
+    e_prev = r0[R.SUM_EPS]
+    t = eng.time
+    tot_events = 0
+    for it in range(5):
+        t += 1.0 / nu
+        r = eng.advance(nu, t, sample=True)
+        assert r[R.N_SAMPLED] == n
+        assert r[R.N_NU_EXCEEDED] == 0 and r[R.N_TABLE_CLAMPED] == 0
+        ev = r[R.N_REAL] + r[R.N_NULL]
+        tot_events += ev
+        assert abs(ev / n - 1.0) < 5e-3                               # Poisson(1) events per electron per interval
+        assert r[R.HEADER:R.HEADER + P].sum() == r[R.N_REAL]
+        balance = r[R.GAIN_FIELD] + r[R.HEADER + P:R.HEADER + 2 * P].sum() + r[R.HEADER + 2 * P:R.HEADER + 3 * P].sum() + r[R.GROWTH]
+        # attachment removes the attached electron's energy through the loss term, births add the ejected energy through growth accounting
+        assert abs((r[R.SUM_EPS] - e_prev) - balance) <= 2e-6 * r[R.SUM_EPS]
+        e_prev = r[R.SUM_EPS]
+    eng.close()

@@ -1,0 +1,42 @@
+"""CPU-side checks (no GPU): the C-ABI library loads, exports every symbol include/lokib200.h declares, and refuses to run
+without a device (there is no CPU fallback)."""
+import os
+import re
+
+import pytest
+
+import golden_io as gio
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    import loki_mc_b200 as lk
+    from loki_mc_b200._capi import SYMBOLS
+    if not os.path.exists(lk.lib_path()):
+        lk.build()
+    L = lk.lib()
+    hdr = open(os.path.join(ROOT, "include", "lokib200.h")).read()
+    declared = sorted(set(re.findall(r"\b(lokib200_[a-z0-9_]+)\s*\(", hdr)))
+    assert declared, "no declarations found"
+    for s in declared:
+        assert hasattr(L, s), "missing symbol " + s
+    assert sorted(SYMBOLS) == declared
+    assert L.lokib200_abi_version() == 1
+
+
+def test_no_cpu_fallback():
+    import torch
+    import loki_mc_b200 as lk
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(lk.LokiB200Error, match="no usable CUDA device"):
+        lk.Engine(gio.load("reid_dc"), 128)
+
+
+def test_product_does_not_import_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "loki_mc_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "lokioracle" not in src and "oracle/" not in src, f
