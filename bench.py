@@ -1,0 +1,294 @@
+#!/usr/bin/env python3
+"""bench.py -- collision events/s (real + null, counted as the reference counts them, BoltzmannMC.C:1308-1320) of the electron
+Monte Carlo hot path.
+
+  python bench.py --gpus N --steps K --warmup W            our arm (one process per GPU; torchrun for N > 1)
+  python bench.py --impl reference --gpus N --steps K ...  the reference's own CPU implementation on the host cores
+
+Workload (BASELINE.json configs[1]): N2, DC field, E/N = 100 Td point of the sweep, anisotropic scattering (Born-dipole
+rotational, Surendra excitation, momentum-conserving ionization), 1e7 electrons per GPU, reference cadence: one synchronisation
+interval of 1/nu_trial per step (synchronizationTimeXMaxCollisionFrequency = 1, i.e. on average one trial event per electron per
+step) with the ensemble sums of calculateMeanDataForSwarmParams sampled every step.  The process set comes from
+tests/golden/n2_aniso.npz (flattened by the unmodified reference from its own LXCat input, see oracle/gen_golden.py); the
+ensemble is synthetic: a Maxwellian at the steady-state mean energy, relaxed for --relax intervals before the warm-up.
+
+A "step" = one synchronisation interval over the whole ensemble.  `value` = events of all ranks / device time with the state
+resident in HBM and no host round trip per step; `e2e` = the same through the blocking C-ABI call lokib200_advance_to_sync,
+i.e. with the per-step host <-> device traffic a real driver has (scalars in, result vector out) and the host-side trial-
+frequency logic in the loop.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+STATE_BYTES_PER_EVENT = 128.0   # 8 FP64 state words read + written once per trial event at sync factor 1
+MEAN_ENERGY_EV = {"n2_aniso": 3.9, "reid_dc": 0.269, "air": 2.74, "arhe": 10.2, "o2_sdcs": 3.43}
+KB_OVER_QE = 1.38064852e-23 / 1.6021766208e-19
+
+
+def load_model(name):
+    import golden_io as gio
+    return gio.load(name)
+
+
+class ClockSampler(threading.Thread):
+    """samples SM clocks / throttle reasons of one GPU while the timed region runs (B200_PROFILING.md recipe)"""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._stop_evt = index, [], threading.Event()
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                     stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self._stop_evt.wait(0.2)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=5)
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        reasons = []
+        for name, col in (("hw_slowdown", 3), ("hw_thermal_slowdown", 4), ("sw_thermal_slowdown", 5), ("sw_power_cap", 6)):
+            if any(len(r) > col and r[col].lower().startswith("active") for r in self.rows):
+                reasons.append(name)
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None, reasons=reasons, samples=len(self.rows))
+
+
+def measured_hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def cpu_baseline_port(model_name, mean_energy, n_cpu=200_000, intervals=12):
+    """the oracle (a port of the reference algorithm, OpenMP over electrons like BoltzmannMC.C:636) timed on the host cores on a
+    bounded sample of the same workload: n_cpu electrons, `intervals` synchronisation intervals after 3 warm-up intervals"""
+    from oracle import lokioracle as lo
+    g = load_model(model_name)
+    m = lo.Model(g)
+    ens = lo.Ensemble(m, n_cpu, 12345, 0)
+    ratio = mean_energy / (1.5 * KB_OVER_QE * g["cond"]["gas_temperature"])
+    ens.init(ratio)
+    mx = ens.max_energy()
+    t = m.build_tables(2.0 * mx)
+    nu = float(t["nu_max"][-1])
+    tnow, ev = 0.0, 0
+    for it in range(1, 4):
+        tnow += 1.0 / nu
+        ens.advance(nu, tnow, it, population_control=1)
+    t0 = time.perf_counter()
+    for it in range(4, 4 + intervals):
+        tnow += 1.0 / nu
+        r = ens.advance(nu, tnow, it, population_control=1)
+        ev += r["n_real"] + r["n_null"]
+    dt = time.perf_counter() - t0
+    return dict(value=ev / dt, unit="events/s", cores=os.cpu_count(), kind="port",
+                sample="%d electrons x %d sync intervals (%.3g events) of the same model, oracle/lokioracle.c with OpenMP on all host cores" % (n_cpu, intervals, ev))
+
+
+def run_reference_arm(args):
+    """--impl reference: the reference's own CPU implementation of the path on the host cores (rank 0 only)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    g = load_model(args.model)
+    line = dict(metric="collision_events_per_sec", unit="events/s", n_gpus=args.gpus, steps=args.steps, warmup=args.warmup, higher_is_better=True,
+                scaling="weak", vs_baseline=None, dtype="f64", data="synthetic", impl="reference")
+    from oracle import run_reference as rr
+    n_ref = args.ref_electrons
+    if rr.available():
+        text = str(g["setup_text"])
+        text = text.replace("nElectrons: 1000", "nElectrons: %d" % n_ref).replace("nIntegrationPoints: 1E3", "nIntegrationPoints: %d" % args.ref_points)
+        text = text.replace("output:\n  isOn: false", "output:\n  isOn: true\n  folder: bench_ref\n  dataFiles:\n    - swarmParameters\n    - MCSimDetails")
+        res = rr.run(text, "bench_ref")
+        d = res["jobs"][0]["details"]
+        events = d["total number of real collisions"] + d["total number of null collisions"]
+        elapsed = d["Elapsed time"]
+        n_int = max(1.0, events / n_ref)   # ~ one trial event per electron per synchronisation interval
+        kind, cores = "reference", res["threads"]
+        sample = "unmodified lokimc (oracle/_ref, g++ -O2 -fopenmp) on the %s setup with nElectrons=%d, nIntegrationPoints=%d: whole job incl. relaxation, %.3g events in %.1f s" % (
+            args.model, n_ref, args.ref_points, events, elapsed)
+        mean_e = res["jobs"][0]["swarm"].get("Energy parameters/Mean energy")
+    else:
+        from oracle import lokioracle as lo
+        m = lo.Model(g)
+        r = m.solve(n_ref, 1, args.ref_points)
+        events, elapsed, n_int = r[29] + r[30], r[34], max(1.0, r[33])
+        kind, cores = "port", os.cpu_count()
+        sample = "oracle port lo_solve on the %s model, nElectrons=%d, nIntegrationPoints=%d" % (args.model, n_ref, args.ref_points)
+        mean_e = r[0]
+    value = events / elapsed
+    line.update(value=value, ms_per_step=1e3 * elapsed / n_int,
+                config=dict(workload="N2 DC 100 Td anisotropic (configs[1] point), reference CPU path", model=args.model, electrons=n_ref,
+                            sync_factor=1.0, intervals=n_int, mean_energy_eV=mean_e),
+                cpu_baseline=dict(value=value, unit="events/s", cores=cores, kind=kind, sample=sample),
+                e2e=dict(value=value, unit="events/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--model", default="n2_aniso")
+    ap.add_argument("--electrons", type=float, default=1e7, help="electrons per GPU")
+    ap.add_argument("--relax", type=int, default=60, help="untimed relaxation intervals before the warm-up")
+    ap.add_argument("--ref-electrons", type=int, default=50_000)
+    ap.add_argument("--ref-points", type=int, default=500)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import torch
+    import torch.distributed as dist
+    import loki_mc_b200 as lk
+    R = lk.R
+    rank, world, local = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    g = load_model(args.model)
+    n = int(args.electrons)
+    eng = lk.Engine(g, n, seed=0x4C6F4B49, device=local, first_electron_id=rank * n)
+    stream = torch.cuda.current_stream()
+    eng.set_stream(stream.cuda_stream)
+    P, L = eng.P, lk.result_len(eng.P)
+    mean_e = MEAN_ENERGY_EV.get(args.model, 1.0)
+    ratio = mean_e / (1.5 * KB_OVER_QE * g["cond"]["gas_temperature"])
+    mx = eng.init_ensemble(ratio)
+    eng.build_tables(2.0 * mx)
+    nu = eng.check_nu_trial(mx, eng.table_info()["nu_max_last"], horizon=11.0)
+
+    d_res = torch.zeros(L, dtype=torch.float64, device="cuda")
+    d_max = torch.zeros(2, dtype=torch.float64, device="cuda")
+    d_events = torch.zeros(1, dtype=torch.float64, device="cuda")
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def allreduce_result():
+        # one NCCL all-reduce per sampling interval: SUM part and MAX part of the result vector (include/lokib200.h)
+        if world > 1:
+            d_max.copy_(d_res[R.SUM_COUNT:R.HEADER])
+            d_res[R.SUM_COUNT:R.HEADER] = 0
+            dist.all_reduce(d_res, op=dist.ReduceOp.SUM)
+            dist.all_reduce(d_max, op=dist.ReduceOp.MAX)
+            d_res[R.SUM_COUNT:R.HEADER] = d_max
+
+    def host_step(t):
+        """the blocking C-ABI call with the host-side trial-frequency logic a driver runs every interval"""
+        nonlocal nu, mx
+        nu = eng.check_nu_trial(mx, nu, horizon=11.0)
+        t += 1.0 / nu
+        res = eng.advance(nu, t, sample=True)
+        if world > 1:
+            d_res.copy_(torch.from_numpy(res)); allreduce_result(); res = d_res.cpu().numpy()
+        mx = max(res[R.MAX_EPS], res[R.MAX_EPS_SEEN])
+        return t, res
+
+    # ---- relaxation + warm-up (untimed) ----
+    t = eng.time
+    for _ in range(args.relax + args.warmup):
+        t, res = host_step(t)
+    mean_energy_now = res[R.SUM_EPS] / res[R.N_SAMPLED]
+
+    # ---- timed leg 1: e2e through the blocking C-ABI call ----
+    sampler = ClockSampler(local); sampler.start()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev_e2e = 0.0
+    e0.record()
+    for _ in range(args.steps):
+        t, res = host_step(t)
+        ev_e2e += res[R.N_REAL] + res[R.N_NULL]
+    e1.record()
+    barrier()
+    ms_e2e = e0.elapsed_time(e1)
+
+    # ---- timed leg 2: device-resident (no host round trip inside the region) ----
+    nu = eng.check_nu_trial(mx, nu, horizon=float(args.steps) + 11.0)   # one bound for the whole region
+    eng.kernel_time_ms()                                                 # reset the per-kernel event log
+    launches0 = eng.launch_count()
+    d_events.zero_()
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        t += 1.0 / nu
+        eng.advance_device(nu, t, True, d_res.data_ptr())
+        allreduce_result()
+        d_events += d_res[R.N_REAL] + d_res[R.N_NULL]
+    e1.record()
+    barrier()
+    ms_dev = e0.elapsed_time(e1)
+    clocks = sampler.stop()
+    adv_ms, adv_n = eng.kernel_time_ms()
+    launches = eng.launch_count() - launches0
+    ev_dev = float(d_events.item())   # already the sum over ranks when world > 1
+
+    tm = torch.tensor([ms_dev, ms_e2e], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+    ms_dev, ms_e2e = float(tm[0]), float(tm[1])
+    final = d_res.cpu().numpy()
+    if rank == 0:
+        peak, peak_src = measured_hbm_peak()
+        ev_per_launch_rank = ev_dev / world / args.steps
+        achieved = STATE_BYTES_PER_EVENT * ev_per_launch_rank / (adv_ms * 1e-3) / 1e9 if adv_ms > 0 else None
+        line = dict(
+            metric="collision_events_per_sec", value=ev_dev / (ms_dev * 1e-3), unit="events/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
+            ms_per_step=ms_dev / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64", data="synthetic",
+            config=dict(workload="N2 DC E/N=100 Td anisotropic scattering, 1e7 electrons per GPU, reference cadence (sync factor 1, ensemble sums every interval) [BASELINE.json configs[1]]",
+                        model=args.model, electrons_per_gpu=n, processes=P, sync_factor=1.0, relax_intervals=args.relax,
+                        mean_energy_eV=mean_energy_now, nu_trial=nu, table_mib=round(eng.table_info()["nE"] * ((P + 15) // 16 * 16) * 8 / 2 ** 20, 1),
+                        l2_policy="state 640 MB per GPU >> 126 MB L2: every step streams it from HBM", real_fraction=float(final[R.N_REAL] / (final[R.N_REAL] + final[R.N_NULL]))),
+            e2e=dict(value=ev_e2e / (ms_e2e * 1e-3), unit="events/s", h2d_bytes_per_step=16 * world,
+                     d2h_bytes_per_step=8 * L * world, ms_per_step=ms_e2e / args.steps),
+            gpu_launches=int(launches * world), clocks=clocks,
+            roofline=dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=(achieved / peak) if achieved else None, traffic=None,
+                          kernel="k_advance", kernel_ms=adv_ms, kernel_launches=adv_n, bytes_per_event=STATE_BYTES_PER_EVENT, peak_source=peak_src,
+                          kernel_share_of_step=adv_ms * adv_n / ms_dev if ms_dev > 0 else None))
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                line["cpu_baseline"] = cpu_baseline_port(args.model, mean_e)
+            except Exception as ex:   # the baseline is reported, never required for the GPU number
+                line["cpu_baseline"] = dict(value=None, unit="events/s", cores=os.cpu_count(), kind="port", sample="failed: %s" % ex)
+        print(json.dumps(line))
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
