@@ -140,6 +140,10 @@ int lokib200_set_stream(lokib200_engine* h, void* cuda_stream);
 
 /* --- tables (replaces: allocateEvaluateVariablesFirstTime BMC.C:89-270 hand-off, interpolateCrossSections BMC.C:561-615) --- */
 int lokib200_set_processes(lokib200_engine* h, const lokib200_process_soa* p);
+/* read back what the engine holds (used by the host driver, which sees the engine only through this ABI) */
+int lokib200_get_config(const lokib200_engine* h, lokib200_config* cfg);
+int lokib200_process_count(const lokib200_engine* h);
+int lokib200_get_rel_densities(const lokib200_engine* h, double* rel_density);
 /* host flattening + upload: uniform grid of n_interp_points energies up to max_energy, sigma x relDensity, row cumsum, nu_tot, running max */
 int lokib200_build_tables(lokib200_engine* h, double max_energy);
 /* upload tables built elsewhere (e.g. dumped from the reference object); cum is row-major [nE][P] */
@@ -164,6 +168,8 @@ int lokib200_advance_to_sync(lokib200_engine* h, double nu_trial, double t_sync,
 /* same, asynchronous: the result stays in device memory (`d_result`, >= LOKIB200_RESULT_LEN(P) doubles, caller-owned device
  * pointer, e.g. a torch tensor that is then all-reduced over NCCL); no host synchronisation */
 int lokib200_advance_to_sync_device(lokib200_engine* h, double nu_trial, double t_sync, int32_t sample, double* d_result);
+/* blocking read of the result of the last lokib200_advance_to_sync_device(..., d_result = NULL) call into host memory */
+int lokib200_read_result(lokib200_engine* h, double* result);
 
 /* --- distributions (replaces: getTimeDependDistributions BMC.C:1492-1572, histogramCount / histogram2DCount MathFunctions.C:61-127) ---
  * grids are those of checkSteadyState (BMC.C:1862-1883): energy [0,max_eedf_energy], cos in [-1,1], v_r in [0,v_max], v_z in [-v_max,v_max] */
@@ -177,6 +183,14 @@ int lokib200_fetch_histograms(lokib200_engine* h, double* eeh, double* eah, doub
 int lokib200_step_injected(lokib200_engine* h, int32_t n, const lokib200_electron* in, double nu_trial, const double* t_sync,
                            const double* draws, int32_t n_draws, lokib200_electron* out, lokib200_event_out* ev);
 
+/* ensemble sums of the CURRENT state without advancing (the t = 0 sample of evaluateEEDF, BMC.C:310); fills the SUM_EPS..N_SAMPLED
+ * and MAX_EPS entries of `result`, zeroes the rest */
+int lokib200_sample_moments(lokib200_engine* h, double* result);
+/* getTimeDependDistributions' regrid (BMC.C:1497-1548): new energy grid [0,new_max_eedf_energy] for the EEDF / angular histograms
+ * (the velocity grid is kept, as in the reference); the device accumulators restart from zero and the caller carries the
+ * remapped old counts */
+int lokib200_regrid_energy_histograms(lokib200_engine* h, double new_max_eedf_energy);
+
 /* --- helpers that mirror host-side scalar logic of the path --- */
 /* maximizationAccelerationEnergy (BMC.C:765-802) */
 double lokib200_max_accel_energy(const lokib200_engine* h, double initial_energy, double dt);
@@ -186,6 +200,56 @@ int lokib200_check_nu_trial(lokib200_engine* h, double max_energy, double horizo
 int64_t lokib200_launch_count(const lokib200_engine* h);
 /* average device time [ms] of the advance kernel over the launches since the last call (CUDA events on the engine's stream) */
 int lokib200_kernel_time_ms(lokib200_engine* h, double* advance_ms, int64_t* launches);
+
+
+/* ------------------------------------------------------------------------------------------------------------------------
+ * Host driver of one job: BoltzmannMC::evaluateEEDF (BMC.C:299-426) restated on top of the entry points above, in C++
+ * (loki_mc_b200/host/boltzmann_mc.cpp).  It keeps the reference's control flow: checkMaxCollisionFrequency before every
+ * interval, sampling every `sync_over_sampling` intervals, checkSteadyState (:1787-1893), checkStatisticalErrors (:1743-1767),
+ * the stop criteria (:320-325) and the time averages (:1484-1741).  Several engines (one per GPU, disjoint electron-id ranges)
+ * may be passed: their per-interval result vectors are summed on the host, which is all the exchange the path needs.
+ * ------------------------------------------------------------------------------------------------------------------------ */
+typedef struct lokib200_solve_controls {   /* numericsMC keys, BMC.h:262-365 (values already multiplied by nElectrons where the ctor does) */
+  double n_integration_points;           /* requiredIntegrationPoints */
+  double n_integrated_ss_times;          /* requiredIntegratedSSTimes */
+  double integrated_absolute_time;       /* requiredIntegratedAbsoluteTime */
+  int32_t errors_to_be_checked;          /* numericsMC.relError present */
+  int32_t sync_over_sampling;            /* synchronizationOverSampling (>= 1) */
+  double rel_err_mean_energy, rel_err_flux_drift, rel_err_flux_diff, rel_err_bulk_drift, rel_err_bulk_diff, rel_err_power_balance;
+  double min_collisions_before_ss, max_collisions_before_ss, max_collisions_after_ss;
+  double sync_factor;                    /* synchronizationTimeXMaxCollisionFrequency */
+  double initial_temp_ratio;             /* initialElecTempOverGasTemp */
+  double energy_max_elastic;             /* energyMaxElastic (BMC.C:158) */
+  int64_t max_intervals;                 /* safety stop (0 = none); not a reference key */
+} lokib200_solve_controls;
+
+typedef struct lokib200_solve_results {   /* the public members the reference's sinks read (Output.h:123-147, 794-820) */
+  double averaged_mean_energy, averaged_mean_energy_error;
+  double flux_drift_velocity[3], flux_drift_velocity_error[3];
+  double flux_diffusion[9], flux_diffusion_error[9];
+  double bulk_drift_velocity[3], bulk_drift_velocity_error[3];
+  double bulk_diffusion[9], bulk_diffusion_error[9];
+  double power_gain_field, power_growth, power_balance_rel_error;   /* averagedPowerGainField, averagedPowerGrowth (eV m3 / s per electron) */
+  double time, steady_state_time, total_integrated_time, trial_collision_frequency, max_eedf_energy, elapsed_seconds;
+  double total_collisions, null_collisions, collisions_at_ss, null_collisions_at_ss;
+  int64_t n_sampling_points, n_integration_points, n_sync_points, n_table_rebuilds;
+  int32_t good_statistical_errors, stopped_by_max_collisions;
+} lokib200_solve_results;
+
+typedef struct lokib200_job lokib200_job;
+int lokib200_job_create(lokib200_engine* const* engines, int32_t n_engines, const lokib200_solve_controls* c, lokib200_job** out);
+int lokib200_job_solve(lokib200_job* j, lokib200_solve_results* res);
+/* per-process outputs: averagedRateCoeffs, averagedPowerGainProcesses, averagedPowerLossProcesses, collisionCounters (after steady state) */
+int lokib200_job_process_outputs(const lokib200_job* j, double* rate_coeffs, double* power_gain, double* power_loss, double* counts);
+/* time series (MCTemporalInfo): sampling times, mean energies, mean positions[3], mean velocities[3], position covariances[9] per sample; any may be NULL */
+int64_t lokib200_job_time_series(const lokib200_job* j, double* times, double* mean_energy, double* mean_pos, double* mean_vel, double* pos_cov);
+/* accumulated histograms incl. the carry of earlier grids: eehSum[nE], eahSum[nE][nCos], evhSum[nR][nA], eehSum_periodic[nPh][nE] */
+int lokib200_job_histograms(lokib200_job* j, double* eeh, double* eah, double* evh, double* eeh_periodic);
+/* phase-resolved sums (AC field): nIntegrationPointsPerPhase[nPh], meanEnergies_periodic[nPh], fluxVelocities_periodic[nPh][3],
+ * bulkVelocities_periodic[nPh][3] (already divided by the points per phase, BMC.C:1728-1734) */
+int lokib200_job_periodic(const lokib200_job* j, double* points_per_phase, double* mean_energy, double* flux_velocity, double* bulk_velocity);
+const char* lokib200_job_last_error(const lokib200_job* j);
+void lokib200_job_destroy(lokib200_job* j);
 
 #ifdef __cplusplus
 }

@@ -34,11 +34,12 @@ def lib_path():
 def build(force=False, verbose=False):
     """Compile csrc/lokib200.cu for sm_100a into loki_mc_b200/liblokib200.so (in-tree, so it travels to the GPU box)."""
     out = lib_path()
-    srcs = [os.path.join(SRC, f) for f in ("lokib200.cu", "lk_kernels.cuh", "lk_physics.cuh")] + [os.path.join(ROOT, "include", "lokib200.h")]
+    srcs = [os.path.join(SRC, "lokib200.cu"), os.path.join(PKG, "host", "boltzmann_mc.cpp")] + \
+           [os.path.join(SRC, f) for f in ("lk_tile.cuh", "lk_kernels.cuh", "lk_physics.cuh")] + [os.path.join(ROOT, "include", "lokib200.h")]
     if not force and os.path.exists(out) and all(os.path.getmtime(out) >= os.path.getmtime(s) for s in srcs):
         return out
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", out, srcs[0]]
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", out, srcs[0], srcs[1]]
     subprocess.check_call(cmd)
     return out
 
@@ -76,7 +77,10 @@ SYMBOLS = ["lokib200_abi_version", "lokib200_device_count", "lokib200_create", "
            "lokib200_nu_max_at", "lokib200_init_ensemble", "lokib200_set_ensemble", "lokib200_get_ensemble", "lokib200_time",
            "lokib200_advance_to_sync", "lokib200_advance_to_sync_device", "lokib200_set_histogram_grid", "lokib200_sample_histograms",
            "lokib200_fetch_histograms", "lokib200_step_injected", "lokib200_max_accel_energy", "lokib200_check_nu_trial",
-           "lokib200_launch_count", "lokib200_kernel_time_ms"]
+           "lokib200_launch_count", "lokib200_kernel_time_ms", "lokib200_get_config", "lokib200_process_count", "lokib200_get_rel_densities",
+           "lokib200_sample_moments", "lokib200_regrid_energy_histograms", "lokib200_read_result", "lokib200_job_create", "lokib200_job_solve",
+           "lokib200_job_process_outputs", "lokib200_job_time_series", "lokib200_job_histograms", "lokib200_job_periodic",
+           "lokib200_job_last_error", "lokib200_job_destroy"]
 
 
 def lib():

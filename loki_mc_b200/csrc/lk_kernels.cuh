@@ -31,7 +31,7 @@ constexpr int N_SAMPLE_SUMS = 26;        // R_SUM_EPS .. R_N_SAMPLED
 
 struct State { double *x, *y, *z, *vx, *vy, *vz, *tcf, *nue; };
 
-enum : int { C_BIRTHS = 0, C_DEAD = 1, C_FREED = 2, C_PLACED = 3, C_OVERFLOW = 4, C_TERMS = 5, C_COUNT = 8 };
+enum : int { C_BIRTHS = 0, C_DEAD = 1, C_FREED = 2, C_PLACED = 3, C_OVERFLOW = 4, C_TERMS = 5, C_PENDING = 6, C_COUNT = 8 };
 
 struct Lists {
   double* birth;              // [8][birth_cap]: x y z vx vy vz tcf nue of electrons born inside the interval, already at t_sync
@@ -56,6 +56,12 @@ struct AdvArgs {
   unsigned int interval, pad;
   double nu_trial, t0, t_sync;
 };
+
+// stream of an electron ejected by a parent with stream (c0, c1, k1) that had consumed `used` draws when the ionization was complete
+__device__ __forceinline__ void child_stream(uint32_t c1, uint32_t k1, uint32_t used, uint32_t& cc1, uint32_t& ck1) {
+  cc1 = c1 + ((used + 1u) << 8);
+  ck1 = k1 + 0x632BE5ABu;
+}
 
 // ------------------------------------------------------------------ sampling helpers ------------------------------------------------------------------
 __device__ __forceinline__ double warp_sum(double v) {
@@ -170,7 +176,7 @@ __global__ void __launch_bounds__(ADV_THREADS, 2) k_advance(const Model m, const
 
   unsigned int n_real = 0, n_null = 0, n_born = 0, n_att = 0, n_clamp = 0, n_nuex = 0;
   double gain_field = 0, max_end = 0, max_seen = 0;
-  double stk[CHILD_STACK][7];
+  double stk[CHILD_STACK][8];
 
   const long long n_round = (a.n + 31) & ~31ll;
   for (long long i = blockIdx.x * static_cast<long long>(ADV_THREADS) + threadIdx.x; i < n_round; i += static_cast<long long>(gridDim.x) * ADV_THREADS) {
@@ -213,7 +219,9 @@ __global__ void __launch_bounds__(ADV_THREADS, 2) k_advance(const Model m, const
           if (type == T_IONIZATION) {                                // the ejected electron waits on the thread's stack (BMC.C:1346-1353 semantics:
             ++n_born;                                                 // parent's clock, undefined free time)
             if (sp < CHILD_STACK) {
+              uint32_t cc1, ck1; child_stream(rng.c1, rng.k1, o.used_mark, cc1, ck1);
               stk[sp][0] = o.ejx; stk[sp][1] = o.ejy; stk[sp][2] = o.ejz; stk[sp][3] = o.ejvx; stk[sp][4] = o.ejvy; stk[sp][5] = o.ejvz; stk[sp][6] = p.t;
+              stk[sp][7] = __longlong_as_double(static_cast<long long>(static_cast<unsigned long long>(cc1) | (static_cast<unsigned long long>(ck1) << 32)));
               ++sp;
             } else atomicExch(&L.counters[C_OVERFLOW], 1u);
           } else if (type == T_ATTACHMENT) {
@@ -229,6 +237,8 @@ __global__ void __launch_bounds__(ADV_THREADS, 2) k_advance(const Model m, const
           if (sp > 0) {
             --sp;
             p.x = stk[sp][0]; p.y = stk[sp][1]; p.z = stk[sp][2]; p.vx = stk[sp][3]; p.vy = stk[sp][4]; p.vz = stk[sp][5]; p.t = stk[sp][6];
+            const unsigned long long w = static_cast<unsigned long long>(__double_as_longlong(stk[sp][7]));
+            rng.c1 = static_cast<uint32_t>(w); rng.k1 = static_cast<uint32_t>(w >> 32); rng.used = 0; rng.blk = 0xFFFFFFFFu;
             p.eps = kinetic_eV(p.vx, p.vy, p.vz); p.tcf = NON_DEF; p.nue = a.nu_trial;
             is_child = true;
           } else active = false;
@@ -291,15 +301,24 @@ __global__ void __launch_bounds__(ADV_THREADS) k_sample(const State s, long long
   for (int j = threadIdx.x; j < ADV_WARPS * R_HEADER; j += blockDim.x) (&s_acc[0][0])[j] = 0;
   __syncthreads();
   double max_end = 0;
-  const long long n_round = (n + 31) & ~31ll;
-  for (long long i = blockIdx.x * static_cast<long long>(ADV_THREADS) + threadIdx.x; i < n_round; i += static_cast<long long>(gridDim.x) * ADV_THREADS) {
-    const bool alive = i < n;
-    double x = 0, y = 0, z = 0, vx = 0, vy = 0, vz = 0;
-    if (alive) { x = s.x[i]; y = s.y[i]; z = s.z[i]; vx = s.vx[i]; vy = s.vy[i]; vz = s.vz[i]; }
+  double val[N_SAMPLE_SUMS];
+#pragma unroll
+  for (int j = 0; j < N_SAMPLE_SUMS; ++j) val[j] = 0;
+  for (long long i = blockIdx.x * static_cast<long long>(ADV_THREADS) + threadIdx.x; i < n; i += static_cast<long long>(gridDim.x) * ADV_THREADS) {
+    const double x = __ldcs(&s.x[i]), y = __ldcs(&s.y[i]), z = __ldcs(&s.z[i]), vx = __ldcs(&s.vx[i]), vy = __ldcs(&s.vy[i]), vz = __ldcs(&s.vz[i]);
     const double eps = kinetic_eV(vx, vy, vz);
     max_end = fmax(max_end, eps);
-    sample_moments(alive, x, y, z, vx, vy, vz, eps, s_acc[warp], lane);
-    if (h.enabled && alive) sample_histograms(h, vx, vy, vz, eps, s_eeh);
+    val[0] += eps; val[1] += x; val[2] += y; val[3] += z; val[4] += vx; val[5] += vy; val[6] += vz;
+    val[7] += x * x; val[8] += x * y; val[9] += x * z; val[11] += y * y; val[12] += y * z; val[15] += z * z;
+    val[16] += x * vx; val[17] += x * vy; val[18] += x * vz; val[19] += y * vx; val[20] += y * vy; val[21] += y * vz;
+    val[22] += z * vx; val[23] += z * vy; val[24] += z * vz; val[25] += 1.0;
+    if (h.enabled) sample_histograms(h, vx, vy, vz, eps, s_eeh);
+  }
+#pragma unroll
+  for (int j = 0; j < N_SAMPLE_SUMS; ++j) {
+    if (j == 10 || j == 13 || j == 14) continue;
+    const double sum = warp_sum(val[j]);
+    if (lane == 0) s_acc[warp][R_SUM_EPS + j] = sum;
   }
   const double m0 = warp_max(max_end);
   if (lane == 0) s_acc[warp][R_MAX_EPS] = m0;
@@ -402,22 +421,30 @@ __global__ void k_pc_reset(const Lists L, long long n, double* pc_result) {
 }
 
 // ------------------------------------------------------------------ finalize ------------------------------------------------------------------
-// result[j] = fixed-order combination over blocks of the K1 partials (+ K3 partials for the sampled sums, + K2 growth)
-__global__ void k_finalize(const double* __restrict__ adv_partials, int adv_blocks, const double* __restrict__ smp_partials, int smp_blocks,
-                           const double* __restrict__ pc_result, int P, double* __restrict__ result) {
+// result[j] = fixed-order combination over blocks of the K1 partials (+ the partials of the births pass, + K3 partials for the
+// sampled sums, + K2 growth)
+__global__ void k_finalize(const double* __restrict__ adv_partials, int adv_blocks, const double* __restrict__ birth_partials, int birth_blocks,
+                           const double* __restrict__ smp_partials, int smp_blocks, const double* __restrict__ pc_result, int P,
+                           double* __restrict__ result) {
   const int len = R_HEADER + 3 * P;
-  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < len; j += gridDim.x * blockDim.x) {
-    int src = j;   // symmetric entries of sum r r^T are accumulated once (xy, xz, yz) and mirrored here
-    if (j == R_SUM_RR + 3) src = R_SUM_RR + 1; else if (j == R_SUM_RR + 6) src = R_SUM_RR + 2; else if (j == R_SUM_RR + 7) src = R_SUM_RR + 5;
-    const bool is_max = (j >= R_SUM_COUNT && j < R_HEADER);
-    const bool from_sample = smp_partials && ((j >= R_SUM_EPS && j <= R_N_SAMPLED) || j == R_MAX_EPS);
-    const double* part = from_sample ? smp_partials : adv_partials;
-    const int nb = from_sample ? smp_blocks : adv_blocks;
-    double v = 0;
-    for (int b = 0; b < nb; ++b) { const double t = part[static_cast<size_t>(b) * len + src]; v = is_max ? fmax(v, t) : v + t; }
-    if (j == R_GROWTH && pc_result) v = pc_result[0];
-    result[j] = v;
+  const int j = blockIdx.x;   // one warp per output entry: lanes stride over the blocks, then a fixed-shape shuffle tree
+  if (j >= len) return;
+  const int lane = threadIdx.x;
+  int src = j;   // symmetric entries of sum r r^T are accumulated once (xy, xz, yz) and mirrored here
+  if (j == R_SUM_RR + 3) src = R_SUM_RR + 1; else if (j == R_SUM_RR + 6) src = R_SUM_RR + 2; else if (j == R_SUM_RR + 7) src = R_SUM_RR + 5;
+  const bool is_max = (j >= R_SUM_COUNT && j < R_HEADER);
+  const bool from_sample = smp_partials && ((j >= R_SUM_EPS && j <= R_N_SAMPLED) || j == R_MAX_EPS);
+  double v = 0;
+  if (from_sample) {
+    for (int b = lane; b < smp_blocks; b += 32) { const double t = smp_partials[static_cast<size_t>(b) * len + src]; v = is_max ? fmax(v, t) : v + t; }
+  } else {
+    for (int b = lane; b < adv_blocks; b += 32) { const double t = adv_partials[static_cast<size_t>(b) * len + src]; v = is_max ? fmax(v, t) : v + t; }
+    if (birth_partials)
+      for (int b = lane; b < birth_blocks; b += 32) { const double t = birth_partials[static_cast<size_t>(b) * len + src]; v = is_max ? fmax(v, t) : v + t; }
   }
+  v = is_max ? warp_max(v) : warp_sum(v);
+  if (j == R_GROWTH && pc_result) v = pc_result[0];
+  if (lane == 0) result[j] = v;
 }
 
 // ------------------------------------------------------------------ parity entry ------------------------------------------------------------------

@@ -9,11 +9,12 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
 
-#include "lk_kernels.cuh"
+#include "lk_tile.cuh"
 
 using namespace lk;
 
@@ -58,9 +59,12 @@ struct lokib200_engine {
   double time = 0;
   uint32_t interval = 0;
   Lists lists{};
-  double *d_adv_part = nullptr, *d_smp_part = nullptr, *d_result = nullptr, *d_pc_result = nullptr, *h_result = nullptr;
+  Pending pend{};
+  double *d_adv_part = nullptr, *d_birth_part = nullptr, *d_smp_part = nullptr, *d_result = nullptr, *d_pc_result = nullptr, *h_result = nullptr;
   unsigned long long* d_maxbits = nullptr;
-  int adv_blocks = 0, smp_blocks = 0, part_len = 0;
+  int adv_blocks = 0, tile_blocks = 0, birth_blocks = 0, smp_blocks = 0, part_len = 0;
+  bool use_tile = false;
+  int last_adv_blocks = 0;
 
   // histograms
   HistGrid hist{};
@@ -172,6 +176,56 @@ int launch_advance(lokib200_engine* h, bool sample, const Model& m, const AdvArg
   }
 }
 
+template <int F, int G, bool S>
+int launch_tile_t(lokib200_engine* h, const Model& m, const AdvArgs& a, const HistGrid& hg) {
+  const size_t smem = tile_smem_bytes(h->P, (S && hg.enabled) ? hg.nEn : 0);
+  CK(cudaFuncSetAttribute(k_advance_tile<F, G, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  CK(cudaFuncSetAttribute(k_advance_tile<F, G, S>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  k_advance_tile<F, G, S><<<h->tile_blocks, TILE_THREADS, smem, h->stream>>>(m, h->st, h->lists, h->pend, a, hg, h->d_adv_part);
+  return 0;
+}
+template <int F, int G>
+int launch_tile_s(lokib200_engine* h, bool sample, const Model& m, const AdvArgs& a, const HistGrid& hg) {
+  return sample ? launch_tile_t<F, G, true>(h, m, a, hg) : launch_tile_t<F, G, false>(h, m, a, hg);
+}
+template <int F>
+int launch_tile_g(lokib200_engine* h, int gt, bool sample, const Model& m, const AdvArgs& a, const HistGrid& hg) {
+  switch (gt) {
+    case GT_FALSE: return launch_tile_s<F, GT_FALSE>(h, sample, m, a, hg);
+    case GT_TRUE: return launch_tile_s<F, GT_TRUE>(h, sample, m, a, hg);
+    default: return launch_tile_s<F, GT_SMART>(h, sample, m, a, hg);
+  }
+}
+int launch_tile(lokib200_engine* h, bool sample, const Model& m, const AdvArgs& a, const HistGrid& hg) {
+  switch (field_case(h->cfg)) {
+    case F_DC: return launch_tile_g<F_DC>(h, h->cfg.gas_temperature_effect, sample, m, a, hg);
+    case F_AC: return launch_tile_g<F_AC>(h, h->cfg.gas_temperature_effect, sample, m, a, hg);
+    case F_DCB: return launch_tile_g<F_DCB>(h, h->cfg.gas_temperature_effect, sample, m, a, hg);
+    case F_ECR: return launch_tile_g<F_ECR>(h, h->cfg.gas_temperature_effect, sample, m, a, hg);
+    default: return launch_tile_g<F_ACB>(h, h->cfg.gas_temperature_effect, sample, m, a, hg);
+  }
+}
+
+template <int F>
+void launch_births_g(lokib200_engine* h, int gt, const Model& m, const AdvArgs& a) {
+  const size_t smem = static_cast<size_t>(h->P) * 20 + 16;
+  switch (gt) {
+    case GT_FALSE: k_advance_births<F, GT_FALSE><<<h->birth_blocks, 128, smem, h->stream>>>(m, h->lists, h->pend, a, h->d_birth_part); break;
+    case GT_TRUE: k_advance_births<F, GT_TRUE><<<h->birth_blocks, 128, smem, h->stream>>>(m, h->lists, h->pend, a, h->d_birth_part); break;
+    default: k_advance_births<F, GT_SMART><<<h->birth_blocks, 128, smem, h->stream>>>(m, h->lists, h->pend, a, h->d_birth_part); break;
+  }
+}
+void launch_births(lokib200_engine* h, const Model& m, const AdvArgs& a) {
+  const int gt = h->cfg.gas_temperature_effect;
+  switch (field_case(h->cfg)) {
+    case F_DC: launch_births_g<F_DC>(h, gt, m, a); break;
+    case F_AC: launch_births_g<F_AC>(h, gt, m, a); break;
+    case F_DCB: launch_births_g<F_DCB>(h, gt, m, a); break;
+    case F_ECR: launch_births_g<F_ECR>(h, gt, m, a); break;
+    default: launch_births_g<F_ACB>(h, gt, m, a); break;
+  }
+}
+
 template <int F>
 void launch_injected_g(lokib200_engine* h, int gt, const Model& m, int n, const ElectronIO* in, double nu, const double* ts, const double* dr, int nd,
                        ElectronIO* out, EventIO* ev) {
@@ -261,7 +315,7 @@ void lokib200_destroy(lokib200_engine* h) {
   if (h->stream) cudaStreamSynchronize(h->stream);
   void* ptrs[] = {h->d_type, h->d_angular, h->d_gas_first, h->d_gas_last, h->d_ap0, h->d_ap1, h->d_mass, h->d_redmass, h->d_eloss, h->d_thstd, h->d_wpar,
                   h->d_gas_fraction, h->d_cum, h->d_nu_tot, h->d_state, h->lists.birth, h->lists.dead, h->lists.freed, h->lists.claim, h->lists.dead_flag,
-                  h->lists.growth_terms, h->lists.counters, h->d_adv_part, h->d_smp_part, h->d_result, h->d_pc_result, h->d_maxbits, h->d_eeh, h->d_eah,
+                  h->lists.growth_terms, h->lists.counters, h->pend.col, h->d_adv_part, h->d_birth_part, h->d_smp_part, h->d_result, h->d_pc_result, h->d_maxbits, h->d_eeh, h->d_eah,
                   h->d_evh, h->d_eeh_per};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (h->h_result) cudaFreeHost(h->h_result);
@@ -312,10 +366,17 @@ int lokib200_set_processes(lokib200_engine* h, const lokib200_process_soa* p) {
   h->part_len = R_HEADER + 3 * P;
   int per_sm = 2;
   h->adv_blocks = static_cast<int>(std::min<int64_t>((h->cfg.n_electrons + ADV_THREADS - 1) / ADV_THREADS, static_cast<int64_t>(h->sm_count) * per_sm));
+  h->tile_blocks = static_cast<int>(std::min<int64_t>((h->cfg.n_electrons + TILE - 1) / TILE, static_cast<int64_t>(h->sm_count) * 2));
+  h->birth_blocks = h->sm_count;
   h->smp_blocks = static_cast<int>(std::min<int64_t>((h->cfg.n_electrons + ADV_THREADS - 1) / ADV_THREADS, static_cast<int64_t>(h->sm_count) * 4));
-  for (double** q : {&h->d_adv_part, &h->d_smp_part, &h->d_result}) if (*q) { cudaFree(*q); *q = nullptr; }
+  // kernel choice: the tile kernel needs enough tiles to fill the machine; LOKIB200_KERNEL=thread|tile overrides
+  h->use_tile = h->cfg.n_electrons >= static_cast<int64_t>(TILE) * h->sm_count;
+  if (const char* env = std::getenv("LOKIB200_KERNEL")) { if (!std::strcmp(env, "thread")) h->use_tile = false; else if (!std::strcmp(env, "tile")) h->use_tile = true; }
+  if (tile_smem_bytes(P, h->cfg.n_energy_cells) > 110 * 1024) h->use_tile = false;   // > 2 CTAs/SM worth of shared memory: fall back
+  for (double** q : {&h->d_adv_part, &h->d_birth_part, &h->d_smp_part, &h->d_result}) if (*q) { cudaFree(*q); *q = nullptr; }
   if (h->h_result) { cudaFreeHost(h->h_result); h->h_result = nullptr; }
-  CK(cudaMalloc(&h->d_adv_part, static_cast<size_t>(h->adv_blocks) * h->part_len * sizeof(double)));
+  CK(cudaMalloc(&h->d_adv_part, static_cast<size_t>(std::max(h->adv_blocks, h->tile_blocks)) * h->part_len * sizeof(double)));
+  CK(cudaMalloc(&h->d_birth_part, static_cast<size_t>(h->birth_blocks) * h->part_len * sizeof(double)));
   CK(cudaMalloc(&h->d_smp_part, static_cast<size_t>(h->smp_blocks) * h->part_len * sizeof(double)));
   CK(cudaMalloc(&h->d_result, h->part_len * sizeof(double)));
   CK(cudaMallocHost(&h->h_result, h->part_len * sizeof(double)));
@@ -335,6 +396,9 @@ int lokib200_set_processes(lokib200_engine* h, const lokib200_process_soa* p) {
   CK(cudaMalloc(&L.dead, static_cast<size_t>(L.dead_cap) * sizeof(unsigned int)));
   CK(cudaMalloc(&L.freed, static_cast<size_t>(L.birth_cap) * sizeof(unsigned int)));
   CK(cudaMalloc(&L.growth_terms, (static_cast<size_t>(L.birth_cap) + L.dead_cap) * sizeof(double)));
+  if (h->pend.col) { cudaFree(h->pend.col); h->pend.col = nullptr; }
+  h->pend.cap = L.birth_cap;
+  CK(cudaMalloc(&h->pend.col, 9ull * h->pend.cap * sizeof(double)));
   const size_t n_claim = h->has_pc ? n + L.birth_cap : 1, n_flag = h->has_pc ? n : 1;
   CK(cudaMalloc(&L.claim, n_claim * sizeof(unsigned int)));
   CK(cudaMemset(L.claim, 0, n_claim * sizeof(unsigned int)));
@@ -343,6 +407,14 @@ int lokib200_set_processes(lokib200_engine* h, const lokib200_process_soa* p) {
   h->have_processes = true;
   h->have_tables = false;
   h->maxE = LOKIB200_NON_DEF;
+  return 0;
+}
+
+int lokib200_get_config(const lokib200_engine* h, lokib200_config* cfg) { if (!h || !cfg) return LOKIB200_ERR_INVALID; *cfg = h->cfg; return 0; }
+int lokib200_process_count(const lokib200_engine* h) { return (h && h->have_processes) ? h->P : 0; }
+int lokib200_get_rel_densities(const lokib200_engine* h, double* rd) {
+  if (!h || !rd || !h->have_processes) return LOKIB200_ERR_INVALID;
+  std::memcpy(rd, h->reldens.data(), sizeof(double) * h->P);
   return 0;
 }
 
@@ -491,11 +563,14 @@ int lokib200_advance_to_sync_device(lokib200_engine* h, double nu_trial, double 
     e0 = h->ev_pool[h->ev_used].first; e1 = h->ev_pool[h->ev_used].second; ++h->ev_used;
     CK(cudaEventRecord(e0, h->stream));
   }
-  if ((rc = launch_advance(h, fused, m, a, no_hist))) return rc;
+  if (h->use_tile) { if ((rc = launch_tile(h, fused, m, a, no_hist))) return rc; h->last_adv_blocks = h->tile_blocks; }
+  else { if ((rc = launch_advance(h, fused, m, a, no_hist))) return rc; h->last_adv_blocks = h->adv_blocks; }
   if (h->timing) CK(cudaEventRecord(e1, h->stream));
   ++h->launches;
   CK(cudaGetLastError());
   const double* smp = nullptr;
+  const double* births = nullptr;
+  if (h->has_pc && h->use_tile) { launch_births(h, m, a); ++h->launches; births = h->d_birth_part; CK(cudaGetLastError()); }
   if (h->has_pc) {
     const int pcb = std::max(1, std::min(h->sm_count * 2, static_cast<int>((h->lists.birth_cap + 255) / 256)));
     k_pc_fill<<<pcb, 256, 0, h->stream>>>(h->st, h->lists);
@@ -510,23 +585,59 @@ int lokib200_advance_to_sync_device(lokib200_engine* h, double nu_trial, double 
       smp = h->d_smp_part;
     }
   }
-  k_finalize<<<(h->part_len + 127) / 128, 128, 0, h->stream>>>(h->d_adv_part, h->adv_blocks, smp, h->smp_blocks, h->has_pc ? h->d_pc_result : nullptr, h->P,
-                                                                 d_result ? d_result : h->d_result);
+  k_finalize<<<h->part_len, 32, 0, h->stream>>>(h->d_adv_part, h->last_adv_blocks, births, h->birth_blocks, smp, h->smp_blocks,
+                                                h->has_pc ? h->d_pc_result : nullptr, h->P, d_result ? d_result : h->d_result);
   ++h->launches;
   CK(cudaGetLastError());
   h->time = t_sync;
   return 0;
 }
 
-int lokib200_advance_to_sync(lokib200_engine* h, double nu_trial, double t_sync, int32_t sample, double* result) {
-  int rc = lokib200_advance_to_sync_device(h, nu_trial, t_sync, sample, nullptr);
-  if (rc) return rc;
+int lokib200_read_result(lokib200_engine* h, double* result) {
+  if (!h || !h->d_result) return LOKIB200_ERR_INVALID;
+  CK(cudaSetDevice(h->cfg.device));
   CK(cudaMemcpyAsync(h->h_result, h->d_result, h->part_len * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   double pc[2] = {0, 0};
   if (h->has_pc) CK(cudaMemcpyAsync(pc, h->d_pc_result, sizeof(pc), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
   if (result) std::memcpy(result, h->h_result, h->part_len * sizeof(double));
   if (pc[1] != 0) return fail(h, LOKIB200_ERR_OVERFLOW, "birth/death list overflow inside one synchronisation interval");
+  return 0;
+}
+
+int lokib200_advance_to_sync(lokib200_engine* h, double nu_trial, double t_sync, int32_t sample, double* result) {
+  int rc = lokib200_advance_to_sync_device(h, nu_trial, t_sync, sample, nullptr);
+  if (rc) return rc;
+  return lokib200_read_result(h, result);
+}
+
+int lokib200_sample_moments(lokib200_engine* h, double* result) {
+  int rc = ensure_ready(h, false);
+  if (rc) return rc;
+  CK(cudaSetDevice(h->cfg.device));
+  HistGrid no_hist{};
+  CK(cudaMemsetAsync(h->d_adv_part, 0, static_cast<size_t>(h->adv_blocks) * h->part_len * sizeof(double), h->stream));
+  k_sample<<<h->smp_blocks, ADV_THREADS, 16, h->stream>>>(h->st, h->cfg.n_electrons, no_hist, h->P, h->d_smp_part);
+  k_finalize<<<h->part_len, 32, 0, h->stream>>>(h->d_adv_part, h->adv_blocks, nullptr, 0, h->d_smp_part, h->smp_blocks, nullptr, h->P, h->d_result);
+  h->launches += 2;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(h->h_result, h->d_result, h->part_len * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  if (result) std::memcpy(result, h->h_result, h->part_len * sizeof(double));
+  return 0;
+}
+
+int lokib200_regrid_energy_histograms(lokib200_engine* h, double new_max) {
+  int rc = ensure_ready(h, false);
+  if (rc) return rc;
+  if (!h->hist.enabled || !(new_max > 0)) return fail(h, LOKIB200_ERR_INVALID, "no histogram grid / bad energy");
+  CK(cudaSetDevice(h->cfg.device));
+  HistGrid& g = h->hist;
+  g.e_step = (0.0 + 1 * (new_max - 0.0) / static_cast<double>(g.nEn)) - 0.0;   // BMC.C:1507-1508
+  h->max_eedf_energy = new_max;
+  const size_t ne = g.nEn;
+  CK(cudaMemsetAsync(h->d_eeh, 0, ne * 8, h->stream)); CK(cudaMemsetAsync(h->d_eah, 0, ne * g.nC * 8, h->stream));
+  CK(cudaMemsetAsync(h->d_eeh_per, 0, ne * h->cfg.n_phases * 8, h->stream));
   return 0;
 }
 

@@ -180,6 +180,9 @@ typedef struct {
   uint32_t used;
 } draws_t;
 
+/* counter mode only: every free-time draw starts on an even draw index, so that the (t_cf, R) pair of a null event is ONE Philox call */
+static inline void align_draws(draws_t* d) { if (!d->inj && (d->used & 1u)) ++d->used; }
+
 static inline double draw(draws_t* d) {
   double u;
   if (d->inj) u = ((int)d->used < d->n_inj) ? d->inj[d->used] : 0.5;
@@ -425,7 +428,7 @@ static int collide(const lo_model* m, double nu_e, const double r[3], double v[3
 /* one pass of the loop body BMC.C:637-681 for one electron.  st = [x y z vx vy vz eps t_e t_cf nu_e] */
 static int event(const lo_model* m, double nu_trial, double t_sync, double* st, draws_t* d, coll_out* o, double* gain_field) {
   double *r = st, *v = st + 3, *eps = st + 6, *t_e = st + 7, *t_cf = st + 8, *nu_e = st + 9;
-  if (*t_cf == LO_NON_DEF) { *t_cf = -log(draw(d)) / nu_trial; *nu_e = nu_trial; }   /* :650-655 */
+  if (*t_cf == LO_NON_DEF) { align_draws(d); *t_cf = -log(draw(d)) / nu_trial; *nu_e = nu_trial; }   /* :650-655 */
   if (*t_e + *t_cf > t_sync) {                                        /* :657-663 */
     const double dt = t_sync - *t_e;
     *gain_field = flight(m, *t_e, dt, r, v, eps);
@@ -435,6 +438,7 @@ static int event(const lo_model* m, double nu_trial, double t_sync, double* st, 
   *gain_field = flight(m, *t_e, *t_cf, r, v, eps);                    /* :666-675 */
   *t_e += *t_cf;
   const int chosen = collide(m, *nu_e, r, v, eps, d, o);
+  align_draws(d);
   *t_cf = -log(draw(d)) / nu_trial;
   *nu_e = nu_trial;
   return chosen;

@@ -267,3 +267,46 @@ def test_full_size_energy_balance(name, n):
         assert abs((r[R.SUM_EPS] - e_prev) - balance) <= 2e-6 * r[R.SUM_EPS]
         e_prev = r[R.SUM_EPS]
     eng.close()
+
+
+@pytest.mark.parametrize("name,e_hi,maxE", [("reid_dc", 5.0, 12.0), ("reid_ac", 5.0, 12.0), ("reid_b", 5.0, 12.0), ("reid_ecr", 5.0, 12.0),
+                                             ("reid_acb", 5.0, 12.0), ("reid_true_aniso", 3.0, 8.0), ("n2_aniso", 60.0, 150.0),
+                                             ("arhe_true", 60.0, 150.0), ("air", 40.0, 100.0), ("ls_att_aniso", 40.0, 100.0)])
+def test_tile_kernel_equals_thread_kernel(name, e_hi, maxE, monkeypatch):
+    """the shared-memory tile kernel (compacted event rounds) and the one-thread-per-electron kernel consume the same per-electron
+    draw streams, so they must produce the same ensemble bit for bit and the same event counters -- also when electrons are
+    born (ionization) or lost (attachment): only the slots touched by the population control at t_sync may differ."""
+    import loki_mc_b200 as lk
+    R = lk.R
+    g = gio.load(name)
+    n = 300_000 + 77            # not a multiple of the tile size
+    rng = np.random.default_rng(99)
+    s0 = _start_state(g, n, rng, 1e-2, e_hi)
+    out = {}
+    for kern in ("thread", "tile"):
+        monkeypatch.setenv("LOKIB200_KERNEL", kern)
+        eng = _engine(g, n, seed=4242, first_electron_id=10)
+        eng.build_tables(maxE)
+        nu = eng.table_info()["nu_max_last"]
+        eng.set_ensemble(s0, 0.0)
+        res = [eng.advance(nu, it / nu, sample=True) for it in range(1, 4)]
+        out[kern] = (eng.get_ensemble(), res)
+        eng.close()
+    P = len(g["p_type"])
+    touched = 0
+    for ra, rb in zip(out["thread"][1], out["tile"][1]):
+        for j in (R.N_REAL, R.N_NULL, R.N_BORN, R.N_ATTACHED, R.N_SAMPLED, R.N_TABLE_CLAMPED, R.N_NU_EXCEEDED):
+            assert ra[j] == rb[j], j
+        assert np.array_equal(ra[R.HEADER:R.HEADER + P], rb[R.HEADER:R.HEADER + P])
+        assert abs(ra[R.GAIN_FIELD] - rb[R.GAIN_FIELD]) <= 1e-10 * abs(ra[R.SUM_EPS])
+        assert np.allclose(ra[R.HEADER + P:], rb[R.HEADER + P:], rtol=1e-9, atol=1e-12 * abs(ra[R.SUM_EPS]))
+        touched += int(ra[R.N_BORN] + ra[R.N_ATTACHED])
+    sa, sb = out["thread"][0], out["tile"][0]
+    differ = np.any(sa != sb, axis=0).sum()
+    if touched == 0:
+        assert differ == 0
+        assert np.array_equal(out["thread"][1][-1][:R.N_SAMPLED + 1][R.SUM_EPS:], out["tile"][1][-1][:R.N_SAMPLED + 1][R.SUM_EPS:]) or \
+            np.allclose(out["thread"][1][-1][R.SUM_EPS:R.N_SAMPLED + 1], out["tile"][1][-1][R.SUM_EPS:R.N_SAMPLED + 1], rtol=1e-12)
+    else:
+        assert differ <= 2 * touched + 8
+        assert np.allclose(out["thread"][1][-1][R.SUM_EPS], out["tile"][1][-1][R.SUM_EPS], rtol=1e-3)
