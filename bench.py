@@ -180,7 +180,10 @@ def main():
     g = load_model(args.model)
     n = int(args.electrons)
     eng = lk.Engine(g, n, seed=0x4C6F4B49, device=local, first_electron_id=rank * n)
-    stream = torch.cuda.current_stream()
+    # everything (engine kernels, NCCL all-reduces, timing events) runs on ONE explicit non-default torch stream
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
     eng.set_stream(stream.cuda_stream)
     P, L = eng.P, lk.result_len(eng.P)
     mean_e = MEAN_ENERGY_EV.get(args.model, 1.0)

@@ -35,7 +35,7 @@ def build(force=False, verbose=False):
     """Compile csrc/lokib200.cu for sm_100a into loki_mc_b200/liblokib200.so (in-tree, so it travels to the GPU box)."""
     out = lib_path()
     srcs = [os.path.join(SRC, "lokib200.cu"), os.path.join(PKG, "host", "boltzmann_mc.cpp")] + \
-           [os.path.join(SRC, f) for f in ("lk_tile.cuh", "lk_kernels.cuh", "lk_physics.cuh")] + [os.path.join(ROOT, "include", "lokib200.h")]
+           [os.path.join(SRC, f) for f in ("lk_stream.cuh", "lk_tile.cuh", "lk_kernels.cuh", "lk_physics.cuh")] + [os.path.join(ROOT, "include", "lokib200.h")]
     if not force and os.path.exists(out) and all(os.path.getmtime(out) >= os.path.getmtime(s) for s in srcs):
         return out
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")

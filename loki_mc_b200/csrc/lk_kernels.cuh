@@ -141,6 +141,11 @@ __device__ __forceinline__ void write_partials(double (*s_acc)[R_HEADER], const 
 
 // ------------------------------------------------------------------ K0 ------------------------------------------------------------------
 // evaluateNonConstantVariables, ensemble part (BMC.C:491-508): r = 0, v ~ Maxwellian(sd) via unitNormalRand3 (Math.C:54-59), t_cf undefined
+__global__ void k_identity_ids(unsigned long long* id, long long n, unsigned long long first_id) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n; i += static_cast<long long>(gridDim.x) * blockDim.x)
+    id[i] = first_id + static_cast<unsigned long long>(i);
+}
+
 __global__ void __launch_bounds__(256) k_init_ensemble(State s, long long n, unsigned long long first_id, unsigned long long seed, double sd,
                                                         unsigned long long* max_eps_bits) {
   double mx = 0;

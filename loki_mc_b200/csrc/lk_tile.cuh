@@ -72,6 +72,7 @@ __device__ __forceinline__ void tally_collisions(int chosen, double dE, unsigned
   }
 }
 
+#ifdef LK_BUILD_TILE_KERNEL   // superseded by k_advance_stream (lk_stream.cuh); kept as the measured stepping stone of profiles/r1_v2_*
 template <int FIELD, int GT, bool SAMPLE>
 __global__ void __launch_bounds__(TILE_THREADS, 2) k_advance_tile(const Model m, const State s, const Lists L, const Pending pend, const AdvArgs a,
                                                                    const HistGrid h, double* __restrict__ partials) {
@@ -296,6 +297,8 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) k_advance_tile(const Model m,
   write_partials(s_acc, s_cnt, s_gain, s_loss, m.P, partials);
   if (SAMPLE && h.enabled) flush_energy_histogram(h, s_eeh);
 }
+
+#endif  // LK_BUILD_TILE_KERNEL
 
 // Electrons ejected inside the interval: advance each from its birth time to t_sync (one per thread, they are few), append the
 // survivor to the birth list K2 consumes; their own offspring wait on the thread's stack (BMC.C:1346-1353 semantics).

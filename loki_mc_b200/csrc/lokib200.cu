@@ -14,7 +14,7 @@
 #include <string>
 #include <vector>
 
-#include "lk_tile.cuh"
+#include "lk_stream.cuh"
 
 using namespace lk;
 
@@ -56,6 +56,8 @@ struct lokib200_engine {
   // ensemble
   State st{};
   double* d_state = nullptr;
+  unsigned long long* d_id = nullptr;   // electron id of each slot (the stream kernel permutes electrons inside a CTA's range)
+  bool permuted = false;
   double time = 0;
   uint32_t interval = 0;
   Lists lists{};
@@ -176,33 +178,30 @@ int launch_advance(lokib200_engine* h, bool sample, const Model& m, const AdvArg
   }
 }
 
-template <int F, int G, bool S>
-int launch_tile_t(lokib200_engine* h, const Model& m, const AdvArgs& a, const HistGrid& hg) {
-  const size_t smem = tile_smem_bytes(h->P, (S && hg.enabled) ? hg.nEn : 0);
-  CK(cudaFuncSetAttribute(k_advance_tile<F, G, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-  CK(cudaFuncSetAttribute(k_advance_tile<F, G, S>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-  k_advance_tile<F, G, S><<<h->tile_blocks, TILE_THREADS, smem, h->stream>>>(m, h->st, h->lists, h->pend, a, hg, h->d_adv_part);
+template <int F, int G>
+int launch_stream_t(lokib200_engine* h, const Model& m, const AdvArgs& a, const HistGrid& hg) {
+  const size_t smem = stream_smem_bytes(h->P, 0);
+  CK(cudaFuncSetAttribute(k_advance_stream<F, G, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  CK(cudaFuncSetAttribute(k_advance_stream<F, G, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  const StateId sid{h->st, h->d_id};
+  k_advance_stream<F, G, false><<<h->tile_blocks, STREAM_THREADS, smem, h->stream>>>(m, sid, h->lists, h->pend, a, hg, h->d_adv_part);
   return 0;
 }
-template <int F, int G>
-int launch_tile_s(lokib200_engine* h, bool sample, const Model& m, const AdvArgs& a, const HistGrid& hg) {
-  return sample ? launch_tile_t<F, G, true>(h, m, a, hg) : launch_tile_t<F, G, false>(h, m, a, hg);
-}
 template <int F>
-int launch_tile_g(lokib200_engine* h, int gt, bool sample, const Model& m, const AdvArgs& a, const HistGrid& hg) {
+int launch_stream_g(lokib200_engine* h, int gt, const Model& m, const AdvArgs& a, const HistGrid& hg) {
   switch (gt) {
-    case GT_FALSE: return launch_tile_s<F, GT_FALSE>(h, sample, m, a, hg);
-    case GT_TRUE: return launch_tile_s<F, GT_TRUE>(h, sample, m, a, hg);
-    default: return launch_tile_s<F, GT_SMART>(h, sample, m, a, hg);
+    case GT_FALSE: return launch_stream_t<F, GT_FALSE>(h, m, a, hg);
+    case GT_TRUE: return launch_stream_t<F, GT_TRUE>(h, m, a, hg);
+    default: return launch_stream_t<F, GT_SMART>(h, m, a, hg);
   }
 }
-int launch_tile(lokib200_engine* h, bool sample, const Model& m, const AdvArgs& a, const HistGrid& hg) {
+int launch_stream(lokib200_engine* h, const Model& m, const AdvArgs& a, const HistGrid& hg) {
   switch (field_case(h->cfg)) {
-    case F_DC: return launch_tile_g<F_DC>(h, h->cfg.gas_temperature_effect, sample, m, a, hg);
-    case F_AC: return launch_tile_g<F_AC>(h, h->cfg.gas_temperature_effect, sample, m, a, hg);
-    case F_DCB: return launch_tile_g<F_DCB>(h, h->cfg.gas_temperature_effect, sample, m, a, hg);
-    case F_ECR: return launch_tile_g<F_ECR>(h, h->cfg.gas_temperature_effect, sample, m, a, hg);
-    default: return launch_tile_g<F_ACB>(h, h->cfg.gas_temperature_effect, sample, m, a, hg);
+    case F_DC: return launch_stream_g<F_DC>(h, h->cfg.gas_temperature_effect, m, a, hg);
+    case F_AC: return launch_stream_g<F_AC>(h, h->cfg.gas_temperature_effect, m, a, hg);
+    case F_DCB: return launch_stream_g<F_DCB>(h, h->cfg.gas_temperature_effect, m, a, hg);
+    case F_ECR: return launch_stream_g<F_ECR>(h, h->cfg.gas_temperature_effect, m, a, hg);
+    default: return launch_stream_g<F_ACB>(h, h->cfg.gas_temperature_effect, m, a, hg);
   }
 }
 
@@ -302,6 +301,7 @@ int lokib200_create(const lokib200_config* cfg, lokib200_engine** out) {
   const size_t n = static_cast<size_t>(cfg->n_electrons);
   if ((e = cudaMalloc(&h->d_state, 8 * n * sizeof(double))) != cudaSuccess) return bail("cudaMalloc(state)", e);
   h->st = State{h->d_state, h->d_state + n, h->d_state + 2 * n, h->d_state + 3 * n, h->d_state + 4 * n, h->d_state + 5 * n, h->d_state + 6 * n, h->d_state + 7 * n};
+  if ((e = cudaMalloc(&h->d_id, n * sizeof(unsigned long long))) != cudaSuccess) return bail("cudaMalloc(id)", e);
   if ((e = cudaMalloc(&h->d_maxbits, sizeof(unsigned long long))) != cudaSuccess) return bail("cudaMalloc", e);
   if ((e = cudaMalloc(&h->d_pc_result, 2 * sizeof(double))) != cudaSuccess) return bail("cudaMalloc", e);
   if ((e = cudaMemset(h->d_pc_result, 0, 2 * sizeof(double))) != cudaSuccess) return bail("cudaMemset", e);
@@ -314,7 +314,7 @@ void lokib200_destroy(lokib200_engine* h) {
   cudaSetDevice(h->cfg.device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   void* ptrs[] = {h->d_type, h->d_angular, h->d_gas_first, h->d_gas_last, h->d_ap0, h->d_ap1, h->d_mass, h->d_redmass, h->d_eloss, h->d_thstd, h->d_wpar,
-                  h->d_gas_fraction, h->d_cum, h->d_nu_tot, h->d_state, h->lists.birth, h->lists.dead, h->lists.freed, h->lists.claim, h->lists.dead_flag,
+                  h->d_gas_fraction, h->d_cum, h->d_nu_tot, h->d_state, h->d_id, h->lists.birth, h->lists.dead, h->lists.freed, h->lists.claim, h->lists.dead_flag,
                   h->lists.growth_terms, h->lists.counters, h->pend.col, h->d_adv_part, h->d_birth_part, h->d_smp_part, h->d_result, h->d_pc_result, h->d_maxbits, h->d_eeh, h->d_eah,
                   h->d_evh, h->d_eeh_per};
   for (void* p : ptrs) if (p) cudaFree(p);
@@ -366,13 +366,14 @@ int lokib200_set_processes(lokib200_engine* h, const lokib200_process_soa* p) {
   h->part_len = R_HEADER + 3 * P;
   int per_sm = 2;
   h->adv_blocks = static_cast<int>(std::min<int64_t>((h->cfg.n_electrons + ADV_THREADS - 1) / ADV_THREADS, static_cast<int64_t>(h->sm_count) * per_sm));
-  h->tile_blocks = static_cast<int>(std::min<int64_t>((h->cfg.n_electrons + TILE - 1) / TILE, static_cast<int64_t>(h->sm_count) * 2));
+  h->tile_blocks = static_cast<int>(std::min<int64_t>((h->cfg.n_electrons + POOL - 1) / POOL, static_cast<int64_t>(h->sm_count) * 2));
   h->birth_blocks = h->sm_count;
   h->smp_blocks = static_cast<int>(std::min<int64_t>((h->cfg.n_electrons + ADV_THREADS - 1) / ADV_THREADS, static_cast<int64_t>(h->sm_count) * 4));
   // kernel choice: the tile kernel needs enough tiles to fill the machine; LOKIB200_KERNEL=thread|tile overrides
-  h->use_tile = h->cfg.n_electrons >= static_cast<int64_t>(TILE) * h->sm_count;
-  if (const char* env = std::getenv("LOKIB200_KERNEL")) { if (!std::strcmp(env, "thread")) h->use_tile = false; else if (!std::strcmp(env, "tile")) h->use_tile = true; }
-  if (tile_smem_bytes(P, h->cfg.n_energy_cells) > 110 * 1024) h->use_tile = false;   // > 2 CTAs/SM worth of shared memory: fall back
+  // kernel choice: the streaming-pool kernel needs several pools per CTA to amortise its fill/drain; LOKIB200_KERNEL=thread|stream overrides
+  h->use_tile = h->cfg.n_electrons >= static_cast<int64_t>(4) * POOL * 2 * h->sm_count;
+  if (const char* env = std::getenv("LOKIB200_KERNEL")) { if (!std::strcmp(env, "thread")) h->use_tile = false; else if (!std::strcmp(env, "stream") || !std::strcmp(env, "tile")) h->use_tile = true; }
+  if (stream_smem_bytes(P, 0) > 113 * 1024) h->use_tile = false;   // more than half an SM's shared memory: fall back
   for (double** q : {&h->d_adv_part, &h->d_birth_part, &h->d_smp_part, &h->d_result}) if (*q) { cudaFree(*q); *q = nullptr; }
   if (h->h_result) { cudaFreeHost(h->h_result); h->h_result = nullptr; }
   CK(cudaMalloc(&h->d_adv_part, static_cast<size_t>(std::max(h->adv_blocks, h->tile_blocks)) * h->part_len * sizeof(double)));
@@ -513,7 +514,9 @@ int lokib200_init_ensemble(lokib200_engine* h, double temp_ratio, double* max_en
   CK(cudaMemsetAsync(h->d_maxbits, 0, sizeof(unsigned long long), h->stream));
   const int blocks = static_cast<int>(std::min<int64_t>((h->cfg.n_electrons + 255) / 256, static_cast<int64_t>(h->sm_count) * 8));
   k_init_ensemble<<<blocks, 256, 0, h->stream>>>(h->st, h->cfg.n_electrons, h->cfg.first_electron_id, h->cfg.seed, sd, h->d_maxbits);
-  ++h->launches;
+  k_identity_ids<<<blocks, 256, 0, h->stream>>>(h->d_id, h->cfg.n_electrons, h->cfg.first_electron_id);
+  h->permuted = false;
+  h->launches += 2;
   CK(cudaGetLastError());
   unsigned long long bits = 0;
   CK(cudaMemcpyAsync(&bits, h->d_maxbits, sizeof(bits), cudaMemcpyDeviceToHost, h->stream));
@@ -527,7 +530,11 @@ int lokib200_set_ensemble(lokib200_engine* h, const double* soa8, double time) {
   if (!h || !soa8) return LOKIB200_ERR_INVALID;
   CK(cudaSetDevice(h->cfg.device));
   CK(cudaMemcpyAsync(h->d_state, soa8, 8 * static_cast<size_t>(h->cfg.n_electrons) * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  const int blocks = static_cast<int>(std::min<int64_t>((h->cfg.n_electrons + 255) / 256, static_cast<int64_t>(h->sm_count) * 8));
+  k_identity_ids<<<blocks, 256, 0, h->stream>>>(h->d_id, h->cfg.n_electrons, h->cfg.first_electron_id);
+  ++h->launches;
   CK(cudaStreamSynchronize(h->stream));
+  h->permuted = false;
   h->time = time;
   return 0;
 }
@@ -535,8 +542,23 @@ int lokib200_set_ensemble(lokib200_engine* h, const double* soa8, double time) {
 int lokib200_get_ensemble(lokib200_engine* h, double* soa8) {
   if (!h || !soa8) return LOKIB200_ERR_INVALID;
   CK(cudaSetDevice(h->cfg.device));
-  CK(cudaMemcpyAsync(soa8, h->d_state, 8 * static_cast<size_t>(h->cfg.n_electrons) * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  const size_t n = static_cast<size_t>(h->cfg.n_electrons);
+  if (!h->permuted) {
+    CK(cudaMemcpyAsync(soa8, h->d_state, 8 * n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+  }
+  // the stream kernel permutes electrons inside each CTA's range: return them in electron-id order (index i <-> id first_id + i)
+  std::vector<double> tmp(8 * n);
+  std::vector<unsigned long long> ids(n);
+  CK(cudaMemcpyAsync(tmp.data(), h->d_state, 8 * n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(ids.data(), h->d_id, n * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
+  for (size_t p = 0; p < n; ++p) {
+    const size_t i = static_cast<size_t>(ids[p] - h->cfg.first_electron_id);
+    if (i >= n) return fail(h, LOKIB200_ERR_INVALID, "corrupt electron id column");
+    for (int c = 0; c < 8; ++c) soa8[c * n + i] = tmp[c * n + p];
+  }
   return 0;
 }
 
@@ -563,7 +585,7 @@ int lokib200_advance_to_sync_device(lokib200_engine* h, double nu_trial, double 
     e0 = h->ev_pool[h->ev_used].first; e1 = h->ev_pool[h->ev_used].second; ++h->ev_used;
     CK(cudaEventRecord(e0, h->stream));
   }
-  if (h->use_tile) { if ((rc = launch_tile(h, fused, m, a, no_hist))) return rc; h->last_adv_blocks = h->tile_blocks; }
+  if (h->use_tile) { if ((rc = launch_stream(h, m, a, no_hist))) return rc; h->last_adv_blocks = h->tile_blocks; h->permuted = true; }
   else { if ((rc = launch_advance(h, fused, m, a, no_hist))) return rc; h->last_adv_blocks = h->adv_blocks; }
   if (h->timing) CK(cudaEventRecord(e1, h->stream));
   ++h->launches;
@@ -579,11 +601,11 @@ int lokib200_advance_to_sync_device(lokib200_engine* h, double nu_trial, double 
     k_pc_place<<<pcb, 256, 0, h->stream>>>(h->st, h->lists, a.n);
     k_pc_reset<<<1, 256, 0, h->stream>>>(h->lists, a.n, h->d_pc_result);
     h->launches += 5;
-    if (sample) {
-      k_sample<<<h->smp_blocks, ADV_THREADS, 16, h->stream>>>(h->st, a.n, no_hist, h->P, h->d_smp_part);
-      ++h->launches;
-      smp = h->d_smp_part;
-    }
+  }
+  if (sample && (h->has_pc || h->use_tile)) {   // separate sampling pass (the thread kernel fuses it when nothing can be born or lost)
+    k_sample<<<h->smp_blocks, ADV_THREADS, 16, h->stream>>>(h->st, a.n, no_hist, h->P, h->d_smp_part);
+    ++h->launches;
+    smp = h->d_smp_part;
   }
   k_finalize<<<h->part_len, 32, 0, h->stream>>>(h->d_adv_part, h->last_adv_blocks, births, h->birth_blocks, smp, h->smp_blocks,
                                                 h->has_pc ? h->d_pc_result : nullptr, h->P, d_result ? d_result : h->d_result);

@@ -279,7 +279,7 @@ def test_tile_kernel_equals_thread_kernel(name, e_hi, maxE, monkeypatch):
     import loki_mc_b200 as lk
     R = lk.R
     g = gio.load(name)
-    n = 300_000 + 77            # not a multiple of the tile size
+    n = 1_200_000 + 77          # not a multiple of the pool size; several refills per CTA
     rng = np.random.default_rng(99)
     s0 = _start_state(g, n, rng, 1e-2, e_hi)
     out = {}
@@ -289,24 +289,32 @@ def test_tile_kernel_equals_thread_kernel(name, e_hi, maxE, monkeypatch):
         eng.build_tables(maxE)
         nu = eng.table_info()["nu_max_last"]
         eng.set_ensemble(s0, 0.0)
-        res = [eng.advance(nu, it / nu, sample=True) for it in range(1, 4)]
-        out[kern] = (eng.get_ensemble(), res)
+        res = [eng.advance(nu, 1 / nu, sample=True)]
+        first = eng.get_ensemble()
+        res += [eng.advance(nu, it / nu, sample=True) for it in range(2, 4)]
+        out[kern] = (eng.get_ensemble(), res, first)
         eng.close()
     P = len(g["p_type"])
-    touched = 0
-    for ra, rb in zip(out["thread"][1], out["tile"][1]):
+    # exact agreement holds until the population control reshuffles slots (its victim draws depend on list order), i.e. for the
+    # first interval always, and for all three when nothing is born or lost
+    r1a, r1b = out["thread"][1][0], out["tile"][1][0]
+    touched_first = int(r1a[R.N_BORN] + r1a[R.N_ATTACHED])
+    n_exact = 3 if all(r[R.N_BORN] + r[R.N_ATTACHED] == 0 for r in out["thread"][1]) else 1
+    for ra, rb in list(zip(out["thread"][1], out["tile"][1]))[:n_exact]:
         for j in (R.N_REAL, R.N_NULL, R.N_BORN, R.N_ATTACHED, R.N_SAMPLED, R.N_TABLE_CLAMPED, R.N_NU_EXCEEDED):
             assert ra[j] == rb[j], j
         assert np.array_equal(ra[R.HEADER:R.HEADER + P], rb[R.HEADER:R.HEADER + P])
         assert abs(ra[R.GAIN_FIELD] - rb[R.GAIN_FIELD]) <= 1e-10 * abs(ra[R.SUM_EPS])
         assert np.allclose(ra[R.HEADER + P:], rb[R.HEADER + P:], rtol=1e-9, atol=1e-12 * abs(ra[R.SUM_EPS]))
-        touched += int(ra[R.N_BORN] + ra[R.N_ATTACHED])
     sa, sb = out["thread"][0], out["tile"][0]
     differ = np.any(sa != sb, axis=0).sum()
-    if touched == 0:
+    if n_exact == 3:
         assert differ == 0
-        assert np.array_equal(out["thread"][1][-1][:R.N_SAMPLED + 1][R.SUM_EPS:], out["tile"][1][-1][:R.N_SAMPLED + 1][R.SUM_EPS:]) or \
-            np.allclose(out["thread"][1][-1][R.SUM_EPS:R.N_SAMPLED + 1], out["tile"][1][-1][R.SUM_EPS:R.N_SAMPLED + 1], rtol=1e-12)
+        assert np.allclose(out["thread"][1][-1][R.SUM_EPS:R.N_SAMPLED + 1], out["tile"][1][-1][R.SUM_EPS:R.N_SAMPLED + 1], rtol=1e-12, atol=0)
     else:
-        assert differ <= 2 * touched + 8
-        assert np.allclose(out["thread"][1][-1][R.SUM_EPS], out["tile"][1][-1][R.SUM_EPS], rtol=1e-3)
+        assert touched_first > 0
+        # after the first interval only the slots the population control wrote may differ
+        assert np.any(out["thread"][2] != out["tile"][2], axis=0).sum() <= 2 * touched_first
+        for ra, rb in zip(out["thread"][1], out["tile"][1]):
+            assert ra[R.N_SAMPLED] == n and rb[R.N_SAMPLED] == n
+            assert abs(ra[R.N_REAL] - rb[R.N_REAL]) <= 6 * np.sqrt(ra[R.N_REAL]) and abs(ra[R.SUM_EPS] / rb[R.SUM_EPS] - 1) < 1e-3
