@@ -32,7 +32,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 STATE_BYTES_PER_EVENT = 128.0   # 8 FP64 state words read + written once per trial event at sync factor 1
-MEAN_ENERGY_EV = {"n2_aniso": 3.9, "reid_dc": 0.269, "air": 2.74, "arhe": 10.2, "o2_sdcs": 3.43}
+MEAN_ENERGY_EV = {"n2_aniso": 2.41, "reid_dc": 0.269, "air": 2.74, "arhe": 10.2, "o2_sdcs": 3.43}
 KB_OVER_QE = 1.38064852e-23 / 1.6021766208e-19
 
 

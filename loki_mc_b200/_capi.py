@@ -28,7 +28,8 @@ def result_len(P):
 
 
 def lib_path():
-    return os.path.join(PKG, "liblokib200.so")
+    # LOKIB200_LIB selects an experimental build variant (tools/build_variants.py); the default is the product library
+    return os.environ.get("LOKIB200_LIB") or os.path.join(PKG, "liblokib200.so")
 
 
 def build(force=False, verbose=False):
@@ -64,6 +65,29 @@ class ProcessSoA(C.Structure):
                 ("rel_density", c_dp), ("target_mass", c_dp), ("reduced_mass", c_dp), ("energy_loss", c_dp), ("thermal_std", c_dp),
                 ("w_parameter", c_dp), ("gas_first", c_ip), ("gas_last", c_ip), ("gas_fraction", c_dp), ("xs_offset", c_lp),
                 ("xs_energy", c_dp), ("xs_value", c_dp)]
+
+
+class SolveControls(C.Structure):
+    _fields_ = [("n_integration_points", C.c_double), ("n_integrated_ss_times", C.c_double), ("integrated_absolute_time", C.c_double),
+                ("errors_to_be_checked", C.c_int32), ("sync_over_sampling", C.c_int32),
+                ("rel_err_mean_energy", C.c_double), ("rel_err_flux_drift", C.c_double), ("rel_err_flux_diff", C.c_double),
+                ("rel_err_bulk_drift", C.c_double), ("rel_err_bulk_diff", C.c_double), ("rel_err_power_balance", C.c_double),
+                ("min_collisions_before_ss", C.c_double), ("max_collisions_before_ss", C.c_double), ("max_collisions_after_ss", C.c_double),
+                ("sync_factor", C.c_double), ("initial_temp_ratio", C.c_double), ("energy_max_elastic", C.c_double), ("max_intervals", C.c_int64)]
+
+
+class SolveResults(C.Structure):
+    _fields_ = [("averaged_mean_energy", C.c_double), ("averaged_mean_energy_error", C.c_double),
+                ("flux_drift_velocity", C.c_double * 3), ("flux_drift_velocity_error", C.c_double * 3),
+                ("flux_diffusion", C.c_double * 9), ("flux_diffusion_error", C.c_double * 9),
+                ("bulk_drift_velocity", C.c_double * 3), ("bulk_drift_velocity_error", C.c_double * 3),
+                ("bulk_diffusion", C.c_double * 9), ("bulk_diffusion_error", C.c_double * 9),
+                ("power_gain_field", C.c_double), ("power_growth", C.c_double), ("power_balance_rel_error", C.c_double),
+                ("time", C.c_double), ("steady_state_time", C.c_double), ("total_integrated_time", C.c_double),
+                ("trial_collision_frequency", C.c_double), ("max_eedf_energy", C.c_double), ("elapsed_seconds", C.c_double),
+                ("total_collisions", C.c_double), ("null_collisions", C.c_double), ("collisions_at_ss", C.c_double), ("null_collisions_at_ss", C.c_double),
+                ("n_sampling_points", C.c_int64), ("n_integration_points", C.c_int64), ("n_sync_points", C.c_int64), ("n_table_rebuilds", C.c_int64),
+                ("good_statistical_errors", C.c_int32), ("stopped_by_max_collisions", C.c_int32)]
 
 
 ELECTRON_DTYPE = np.dtype([("r", "f8", 3), ("v", "f8", 3), ("energy", "f8"), ("t", "f8"), ("t_cf", "f8"), ("nu_e", "f8")])
@@ -116,6 +140,20 @@ def lib():
     L.lokib200_check_nu_trial.argtypes = [vp, C.c_double, C.c_double, C.c_double, c_dp]
     L.lokib200_launch_count.argtypes = [vp]; L.lokib200_launch_count.restype = C.c_int64
     L.lokib200_kernel_time_ms.argtypes = [vp, c_dp, c_lp]
+    L.lokib200_sample_moments.argtypes = [vp, c_dp]
+    L.lokib200_regrid_energy_histograms.argtypes = [vp, C.c_double]
+    L.lokib200_read_result.argtypes = [vp, c_dp]
+    L.lokib200_get_config.argtypes = [vp, C.POINTER(Config)]
+    L.lokib200_process_count.argtypes = [vp]
+    L.lokib200_get_rel_densities.argtypes = [vp, c_dp]
+    L.lokib200_job_create.argtypes = [C.POINTER(vp), C.c_int32, C.POINTER(SolveControls), C.POINTER(vp)]
+    L.lokib200_job_solve.argtypes = [vp, C.POINTER(SolveResults)]
+    L.lokib200_job_process_outputs.argtypes = [vp, c_dp, c_dp, c_dp, c_dp]
+    L.lokib200_job_time_series.argtypes = [vp, c_dp, c_dp, c_dp, c_dp, c_dp]; L.lokib200_job_time_series.restype = C.c_int64
+    L.lokib200_job_histograms.argtypes = [vp, c_dp, c_dp, c_dp, c_dp]
+    L.lokib200_job_periodic.argtypes = [vp, c_dp, c_dp, c_dp, c_dp]
+    L.lokib200_job_last_error.argtypes = [vp]; L.lokib200_job_last_error.restype = C.c_char_p
+    L.lokib200_job_destroy.argtypes = [vp]; L.lokib200_job_destroy.restype = None
     _LIB = L
     return L
 
@@ -271,3 +309,68 @@ class Engine:
         ms = C.c_double(); n = C.c_int64()
         self._check(self.L.lokib200_kernel_time_ms(self.h, C.byref(ms), C.byref(n)))
         return ms.value, n.value
+
+
+class Job:
+    """One Monte Carlo job (BoltzmannMC::evaluateEEDF restated in loki_mc_b200/host/boltzmann_mc.cpp) over one or more engines."""
+
+    def __init__(self, engines, n_integration_points=1000, n_integrated_ss_times=0.0, sync_factor=1.0, initial_temp_ratio=0.01,
+                 max_intervals=0, **kw):
+        self.L = lib()
+        self.engines = list(engines)
+        c = SolveControls()
+        c.n_integration_points = float(n_integration_points); c.n_integrated_ss_times = float(n_integrated_ss_times)
+        c.sync_over_sampling = int(kw.get("sync_over_sampling", 1)); c.sync_factor = float(sync_factor)
+        c.initial_temp_ratio = float(initial_temp_ratio); c.energy_max_elastic = float(self.engines[0].energy_max_elastic)
+        c.max_intervals = int(max_intervals)
+        for k in ("rel_err_mean_energy", "rel_err_flux_drift", "rel_err_flux_diff", "rel_err_bulk_drift", "rel_err_bulk_diff", "rel_err_power_balance"):
+            if k in kw:
+                setattr(c, k, float(kw[k])); c.errors_to_be_checked = 1
+        arr = (C.c_void_p * len(self.engines))(*[e.h for e in self.engines])
+        h = C.c_void_p()
+        rc = self.L.lokib200_job_create(arr, len(self.engines), C.byref(c), C.byref(h))
+        if rc != 0:
+            raise LokiB200Error("lokib200_job_create failed (%d)" % rc)
+        self.h = h
+        self.P = self.engines[0].P
+
+    def solve(self):
+        r = SolveResults()
+        rc = self.L.lokib200_job_solve(self.h, C.byref(r))
+        if rc != 0:
+            raise LokiB200Error("lokib200_job_solve failed (%d): %s" % (rc, self.L.lokib200_job_last_error(self.h).decode()))
+        out = {}
+        for name, _ in SolveResults._fields_:
+            v = getattr(r, name)
+            out[name] = np.array(list(v)) if hasattr(v, "__len__") else v
+        return out
+
+    def process_outputs(self):
+        a = [np.zeros(self.P) for _ in range(4)]
+        self.L.lokib200_job_process_outputs(self.h, *[_dp(x) for x in a])
+        return dict(rate_coeffs=a[0], power_gain=a[1], power_loss=a[2], counts=a[3])
+
+    def time_series(self):
+        n = self.L.lokib200_job_time_series(self.h, None, None, None, None, None)
+        t = np.zeros(n); me = np.zeros(n); mp = np.zeros((n, 3)); mv = np.zeros((n, 3)); pc = np.zeros((n, 9))
+        self.L.lokib200_job_time_series(self.h, _dp(t), _dp(me), _dp(mp), _dp(mv), _dp(pc))
+        return dict(times=t, mean_energy=me, mean_position=mp, mean_velocity=mv, position_covariance=pc)
+
+    def histograms(self):
+        c = self.engines[0].cfg
+        eeh = np.zeros(c.n_energy_cells); eah = np.zeros((c.n_energy_cells, c.n_cos_cells)); evh = np.zeros((c.n_radial_cells, c.n_axial_cells))
+        per = np.zeros((c.n_phases, c.n_energy_cells))
+        rc = self.L.lokib200_job_histograms(self.h, _dp(eeh), _dp(eah), _dp(evh), _dp(per))
+        if rc != 0:
+            raise LokiB200Error("no histograms (steady state not reached)")
+        return dict(eeh=eeh, eah=eah, evh=evh, eeh_periodic=per)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.lokib200_job_destroy(self.h); self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

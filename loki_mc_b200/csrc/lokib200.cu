@@ -51,6 +51,9 @@ struct lokib200_engine {
   bool have_tables = false;
   std::vector<double> h_cum, h_nu_tot, h_nu_max;   // host copies (h_cum padded to stride)
   double *d_cum = nullptr, *d_nu_tot = nullptr;
+  double2 *d_pair = nullptr, *d_coarse = nullptr;   // row-pair form of the cumulative table + its coarse level (see lk_physics.cuh)
+  int G = 0, gstride = 0;
+  std::vector<double2> h_pair, h_coarse;
   size_t d_cum_cap = 0;
 
   // ensemble
@@ -113,7 +116,7 @@ Model make_model(const lokib200_engine* h) {
   const lokib200_config& c = h->cfg;
   m.P = h->P; m.stride = h->stride; m.nG = h->nG; m.nE = h->nE;
   m.sharing = c.ionization_sharing; m.sharing_factor = c.energy_sharing_factor;
-  m.Ngas = c.gas_density; m.dE = h->dE;
+  m.Ngas = c.gas_density; m.dE = h->dE; m.inv_dE = (h->dE > 0) ? 1.0 / h->dE : 0.0;
   m.smart_limit = 20.0 * (1.5 * KB * c.gas_temperature / QE);            // BMC.C:433, :916
   const double Ex = c.electric_field[0], Ez = c.electric_field[2], w = c.excitation_omega, W = c.cyclotron_omega;
   m.Ex = Ex; m.Ez = Ez; m.w = w; m.W = W;
@@ -131,6 +134,7 @@ Model make_model(const lokib200_engine* h) {
     }
   }
   m.cum = h->d_cum; m.nu_tot = h->d_nu_tot;
+  m.pair = h->d_pair; m.coarse = h->d_coarse; m.G = h->G; m.gstride = h->gstride;
   m.type = h->d_type; m.angular = h->d_angular; m.ap0 = h->d_ap0; m.ap1 = h->d_ap1; m.mass = h->d_mass; m.redmass = h->d_redmass;
   m.eloss = h->d_eloss; m.thstd = h->d_thstd; m.wpar = h->d_wpar; m.gas_first = h->d_gas_first; m.gas_last = h->d_gas_last;
   m.gas_fraction = h->d_gas_fraction;
@@ -163,18 +167,23 @@ int launch_advance_s(lokib200_engine* h, bool sample, const Model& m, const AdvA
 template <int F>
 int launch_advance_g(lokib200_engine* h, int gt, bool sample, const Model& m, const AdvArgs& a, const HistGrid& hg) {
   switch (gt) {
+#ifndef LK_BENCH_ONLY
     case GT_FALSE: return launch_advance_s<F, GT_FALSE>(h, sample, m, a, hg);
     case GT_TRUE: return launch_advance_s<F, GT_TRUE>(h, sample, m, a, hg);
+#endif
     default: return launch_advance_s<F, GT_SMART>(h, sample, m, a, hg);
   }
 }
 int launch_advance(lokib200_engine* h, bool sample, const Model& m, const AdvArgs& a, const HistGrid& hg) {
   switch (field_case(h->cfg)) {
     case F_DC: return launch_advance_g<F_DC>(h, h->cfg.gas_temperature_effect, sample, m, a, hg);
+#ifndef LK_BENCH_ONLY
     case F_AC: return launch_advance_g<F_AC>(h, h->cfg.gas_temperature_effect, sample, m, a, hg);
     case F_DCB: return launch_advance_g<F_DCB>(h, h->cfg.gas_temperature_effect, sample, m, a, hg);
     case F_ECR: return launch_advance_g<F_ECR>(h, h->cfg.gas_temperature_effect, sample, m, a, hg);
-    default: return launch_advance_g<F_ACB>(h, h->cfg.gas_temperature_effect, sample, m, a, hg);
+    case F_ACB: return launch_advance_g<F_ACB>(h, h->cfg.gas_temperature_effect, sample, m, a, hg);
+#endif
+    default: return launch_advance_g<F_DC>(h, h->cfg.gas_temperature_effect, sample, m, a, hg);
   }
 }
 
@@ -190,18 +199,23 @@ int launch_stream_t(lokib200_engine* h, const Model& m, const AdvArgs& a, const 
 template <int F>
 int launch_stream_g(lokib200_engine* h, int gt, const Model& m, const AdvArgs& a, const HistGrid& hg) {
   switch (gt) {
+#ifndef LK_BENCH_ONLY
     case GT_FALSE: return launch_stream_t<F, GT_FALSE>(h, m, a, hg);
     case GT_TRUE: return launch_stream_t<F, GT_TRUE>(h, m, a, hg);
+#endif
     default: return launch_stream_t<F, GT_SMART>(h, m, a, hg);
   }
 }
 int launch_stream(lokib200_engine* h, const Model& m, const AdvArgs& a, const HistGrid& hg) {
   switch (field_case(h->cfg)) {
     case F_DC: return launch_stream_g<F_DC>(h, h->cfg.gas_temperature_effect, m, a, hg);
+#ifndef LK_BENCH_ONLY
     case F_AC: return launch_stream_g<F_AC>(h, h->cfg.gas_temperature_effect, m, a, hg);
     case F_DCB: return launch_stream_g<F_DCB>(h, h->cfg.gas_temperature_effect, m, a, hg);
     case F_ECR: return launch_stream_g<F_ECR>(h, h->cfg.gas_temperature_effect, m, a, hg);
-    default: return launch_stream_g<F_ACB>(h, h->cfg.gas_temperature_effect, m, a, hg);
+    case F_ACB: return launch_stream_g<F_ACB>(h, h->cfg.gas_temperature_effect, m, a, hg);
+#endif
+    default: return launch_stream_g<F_DC>(h, h->cfg.gas_temperature_effect, m, a, hg);
   }
 }
 
@@ -209,8 +223,10 @@ template <int F>
 void launch_births_g(lokib200_engine* h, int gt, const Model& m, const AdvArgs& a) {
   const size_t smem = static_cast<size_t>(h->P) * 20 + 16;
   switch (gt) {
+#ifndef LK_BENCH_ONLY
     case GT_FALSE: k_advance_births<F, GT_FALSE><<<h->birth_blocks, 128, smem, h->stream>>>(m, h->lists, h->pend, a, h->d_birth_part); break;
     case GT_TRUE: k_advance_births<F, GT_TRUE><<<h->birth_blocks, 128, smem, h->stream>>>(m, h->lists, h->pend, a, h->d_birth_part); break;
+#endif
     default: k_advance_births<F, GT_SMART><<<h->birth_blocks, 128, smem, h->stream>>>(m, h->lists, h->pend, a, h->d_birth_part); break;
   }
 }
@@ -218,10 +234,13 @@ void launch_births(lokib200_engine* h, const Model& m, const AdvArgs& a) {
   const int gt = h->cfg.gas_temperature_effect;
   switch (field_case(h->cfg)) {
     case F_DC: launch_births_g<F_DC>(h, gt, m, a); break;
+#ifndef LK_BENCH_ONLY
     case F_AC: launch_births_g<F_AC>(h, gt, m, a); break;
     case F_DCB: launch_births_g<F_DCB>(h, gt, m, a); break;
     case F_ECR: launch_births_g<F_ECR>(h, gt, m, a); break;
-    default: launch_births_g<F_ACB>(h, gt, m, a); break;
+    case F_ACB: launch_births_g<F_ACB>(h, gt, m, a); break;
+#endif
+    default: launch_births_g<F_DC>(h, gt, m, a); break;
   }
 }
 
@@ -230,8 +249,10 @@ void launch_injected_g(lokib200_engine* h, int gt, const Model& m, int n, const 
                        ElectronIO* out, EventIO* ev) {
   const int blocks = (n + 127) / 128;
   switch (gt) {
+#ifndef LK_BENCH_ONLY
     case GT_FALSE: k_step_injected<F, GT_FALSE><<<blocks, 128, 0, h->stream>>>(m, n, in, nu, ts, dr, nd, out, ev); break;
     case GT_TRUE: k_step_injected<F, GT_TRUE><<<blocks, 128, 0, h->stream>>>(m, n, in, nu, ts, dr, nd, out, ev); break;
+#endif
     default: k_step_injected<F, GT_SMART><<<blocks, 128, 0, h->stream>>>(m, n, in, nu, ts, dr, nd, out, ev); break;
   }
 }
@@ -245,13 +266,34 @@ int ensure_ready(lokib200_engine* h, bool need_tables) {
 
 int push_tables(lokib200_engine* h) {   // h_cum (padded) / h_nu_tot -> device
   const size_t need = static_cast<size_t>(h->nE) * h->stride;
+  h->G = (h->P + 7) / 8; h->gstride = (h->G + 3) / 4 * 4;
+  const size_t need_c = static_cast<size_t>(h->nE) * h->gstride;
   if (need > h->d_cum_cap) {
-    if (h->d_cum) cudaFree(h->d_cum);
-    if (h->d_nu_tot) cudaFree(h->d_nu_tot);
+    for (void* q : {static_cast<void*>(h->d_cum), static_cast<void*>(h->d_nu_tot), static_cast<void*>(h->d_pair), static_cast<void*>(h->d_coarse)}) if (q) cudaFree(q);
     CK(cudaMalloc(&h->d_cum, need * sizeof(double)));
     CK(cudaMalloc(&h->d_nu_tot, static_cast<size_t>(h->nE) * sizeof(double)));
+#ifdef LK_SELECT_2LEVEL
+    CK(cudaMalloc(&h->d_pair, need * sizeof(double2)));
+    CK(cudaMalloc(&h->d_coarse, need_c * sizeof(double2)));
+#else
+    h->d_pair = nullptr; h->d_coarse = nullptr;
+#endif
     h->d_cum_cap = need;
   }
+#ifdef LK_SELECT_2LEVEL
+  // row-pair + coarse forms, derived from the same doubles (no arithmetic: the kernels see identical table values)
+  h->h_pair.resize(need); h->h_coarse.resize(need_c);
+  for (int i = 0; i < h->nE; ++i) {
+    const double* r1 = h->h_cum.data() + static_cast<size_t>(i) * h->stride;
+    const double* r2 = h->h_cum.data() + static_cast<size_t>(std::min(i + 1, h->nE - 1)) * h->stride;
+    double2* pr = h->h_pair.data() + static_cast<size_t>(i) * h->stride;
+    for (int k = 0; k < h->stride; ++k) pr[k] = make_double2(r1[k], r2[k]);
+    double2* cr = h->h_coarse.data() + static_cast<size_t>(i) * h->gstride;
+    for (int g = 0; g < h->gstride; ++g) cr[g] = pr[std::min(8 * g + 7, h->stride - 1)];
+  }
+  CK(cudaMemcpyAsync(h->d_pair, h->h_pair.data(), need * sizeof(double2), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(h->d_coarse, h->h_coarse.data(), need_c * sizeof(double2), cudaMemcpyHostToDevice, h->stream));
+#endif
   CK(cudaMemcpyAsync(h->d_cum, h->h_cum.data(), need * sizeof(double), cudaMemcpyHostToDevice, h->stream));
   CK(cudaMemcpyAsync(h->d_nu_tot, h->h_nu_tot.data(), static_cast<size_t>(h->nE) * sizeof(double), cudaMemcpyHostToDevice, h->stream));
   CK(cudaStreamSynchronize(h->stream));
@@ -314,7 +356,7 @@ void lokib200_destroy(lokib200_engine* h) {
   cudaSetDevice(h->cfg.device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   void* ptrs[] = {h->d_type, h->d_angular, h->d_gas_first, h->d_gas_last, h->d_ap0, h->d_ap1, h->d_mass, h->d_redmass, h->d_eloss, h->d_thstd, h->d_wpar,
-                  h->d_gas_fraction, h->d_cum, h->d_nu_tot, h->d_state, h->d_id, h->lists.birth, h->lists.dead, h->lists.freed, h->lists.claim, h->lists.dead_flag,
+                  h->d_gas_fraction, h->d_cum, h->d_nu_tot, h->d_pair, h->d_coarse, h->d_state, h->d_id, h->lists.birth, h->lists.dead, h->lists.freed, h->lists.claim, h->lists.dead_flag,
                   h->lists.growth_terms, h->lists.counters, h->pend.col, h->d_adv_part, h->d_birth_part, h->d_smp_part, h->d_result, h->d_pc_result, h->d_maxbits, h->d_eeh, h->d_eah,
                   h->d_evh, h->d_eeh_per};
   for (void* p : ptrs) if (p) cudaFree(p);
@@ -737,10 +779,13 @@ int lokib200_step_injected(lokib200_engine* h, int32_t n, const lokib200_electro
   const int gt = h->cfg.gas_temperature_effect;
   switch (field_case(h->cfg)) {
     case F_DC: launch_injected_g<F_DC>(h, gt, m, n, d_in, nu_trial, d_ts, d_dr, n_draws, d_out, d_ev); break;
+#ifndef LK_BENCH_ONLY
     case F_AC: launch_injected_g<F_AC>(h, gt, m, n, d_in, nu_trial, d_ts, d_dr, n_draws, d_out, d_ev); break;
     case F_DCB: launch_injected_g<F_DCB>(h, gt, m, n, d_in, nu_trial, d_ts, d_dr, n_draws, d_out, d_ev); break;
     case F_ECR: launch_injected_g<F_ECR>(h, gt, m, n, d_in, nu_trial, d_ts, d_dr, n_draws, d_out, d_ev); break;
-    default: launch_injected_g<F_ACB>(h, gt, m, n, d_in, nu_trial, d_ts, d_dr, n_draws, d_out, d_ev); break;
+    case F_ACB: launch_injected_g<F_ACB>(h, gt, m, n, d_in, nu_trial, d_ts, d_dr, n_draws, d_out, d_ev); break;
+#endif
+    default: launch_injected_g<F_DC>(h, gt, m, n, d_in, nu_trial, d_ts, d_dr, n_draws, d_out, d_ev); break;
   }
   ++h->launches;
   CK(cudaGetLastError());

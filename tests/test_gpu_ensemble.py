@@ -1,0 +1,63 @@
+"""Ensemble-level parity (BASELINE.json:north_star, second check): swarm parameters of a whole job run by the C++ host driver
+(loki_mc_b200/host/boltzmann_mc.cpp = BoltzmannMC::evaluateEEDF restated) on the GPU engine agree with the UNMODIFIED reference's
+own CPU runs (tests/golden/ensemble_*.json, produced by oracle/gen_ensemble_golden.py from oracle/_ref/lokimc) within 3 sigma.
+
+sigma_eff per quantity = sqrt(sigma_ref^2 + sigma_ours^2) with sigma_ref = max(reference's reported "Rel. std", scatter of the
+reference replicas) (the reported error under-estimates the run-to-run scatter) and sigma_ours the driver's own
+batch-means error.  The GPU run uses 10x the reference's electrons, so the comparison is dominated by the reference's scatter.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import golden_io as gio
+
+pytestmark = pytest.mark.gpu
+
+CASES = ["reid_dc", "reid_acb", "reid_true_aniso", "n2_aniso", "o2_sdcs", "arhe", "air", "ls_f05", "ls_att_aniso"]
+
+
+def _ref(name):
+    return json.load(open(os.path.join(gio.GOLDEN_DIR, "ensemble_%s.json" % name)))
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_swarm_parameters_within_3_sigma(name):
+    import loki_mc_b200 as lk
+    g = gio.load(name)
+    ref = _ref(name)
+    n = 10 * ref["n_electrons"]
+    eng = lk.Engine(g, n, seed=20240 + len(name))
+    job = lk.Job([eng], n_integration_points=ref["n_integration_points"], n_integrated_ss_times=ref["n_integrated_ss_times"])
+    r = job.solve()
+    Ngas = g["cond"]["gas_density"]
+    assert r["steady_state_time"] > 0 and r["n_integration_points"] >= ref["n_integration_points"]
+
+    def check(key, ours, ours_err, floor_rel=0.0):
+        mean, std, rep = ref["mean"][key], ref["std"][key], ref["reported_relstd"][key]
+        sig_ref = max(std, abs(rep * mean), floor_rel * abs(mean))
+        sig = np.sqrt(sig_ref ** 2 + ours_err ** 2)
+        assert abs(ours - mean) <= 3.0 * sig, "%s %s: ours %.6g +- %.2g, reference %.6g +- %.2g (%.1f sigma)" % (name, key, ours, ours_err, mean, sig_ref, abs(ours - mean) / sig)
+
+    check("Energy parameters/Mean energy", r["averaged_mean_energy"], r["averaged_mean_energy_error"])
+    # drift velocity along z (E is along -z for the 180 degree setups); transverse components are zero within noise
+    if abs(ref["mean"]["Flux parameters/v_z"]) > 10 * ref["std"]["Flux parameters/v_z"]:
+        check("Flux parameters/v_z", r["flux_drift_velocity"][2], r["flux_drift_velocity_error"][2])
+        check("Bulk parameters/v_z", r["bulk_drift_velocity"][2], r["bulk_drift_velocity_error"][2])
+    if g["cond"]["cyclotron_omega"] == 0 and g["cond"]["excitation_omega"] == 0:
+        # reduced diffusion coefficients N*D: transverse = (xx+yy)/2, longitudinal = zz (BMC.C:2073-2090 for E along z)
+        fd, fe = r["flux_diffusion"], r["flux_diffusion_error"]
+        check("Flux parameters/Reduced transverse diffusion coefficient", 0.5 * (fd[0] + fd[4]) * Ngas, 0.5 * np.hypot(fe[0], fe[4]) * Ngas, floor_rel=0.004)
+        check("Flux parameters/Reduced longitudinal diffusion coefficient", fd[8] * Ngas, fe[8] * Ngas, floor_rel=0.004)
+        bd, be = r["bulk_diffusion"], r["bulk_diffusion_error"]
+        check("Bulk parameters/Reduced transverse diffusion coefficient", 0.5 * (bd[0] + bd[4]) * Ngas, 0.5 * np.hypot(be[0], be[4]) * Ngas, floor_rel=0.004)
+        check("Bulk parameters/Reduced longitudinal diffusion coefficient", bd[8] * Ngas, be[8] * Ngas, floor_rel=0.004)
+    # real-collision fraction of all events: a property of nu_trial handling and the null-collision method
+    ref_frac = np.mean([x["real"] / (x["real"] + x["null"]) for x in ref["replicas"]])
+    ours_frac = r["total_collisions"] / (r["total_collisions"] + r["null_collisions"])
+    # (depends on the value nu_trial settles at, which differs slightly: our energy bound looks one interval further ahead)
+    assert abs(ours_frac - ref_frac) < 0.25 * ref_frac, (ours_frac, ref_frac)
+    assert r["power_balance_rel_error"] < 5e-3
+    job.close(); eng.close()
