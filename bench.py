@@ -42,34 +42,48 @@ def load_model(name):
 
 
 class ClockSampler(threading.Thread):
-    """samples SM clocks / throttle reasons of one GPU while the timed region runs (B200_PROFILING.md recipe)"""
+    """samples SM clocks / throttle reasons of one GPU through NVML every 10 ms while the timed region runs"""
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.rows, self._stop_evt = index, [], threading.Event()
+        self.index, self.sm, self.mx, self.bits, self._stop_evt = index, [], None, 0, threading.Event()
 
     def run(self):
-        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
-        while not self._stop_evt.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
-                                     stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([x.strip() for x in out.split(",")])
-            except Exception:
-                pass
-            self._stop_evt.wait(0.2)
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[self.index]) if vis and vis.split(",")[self.index].isdigit() else self.index
+            h = nv.nvmlDeviceGetHandleByIndex(phys)
+            self.mx = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            while not self._stop_evt.is_set():
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                self.bits |= int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))
+                self._stop_evt.wait(0.01)
+        except Exception as ex:   # fall back to one nvidia-smi sample
+            self.err = str(ex)
 
     def stop(self):
         self._stop_evt.set()
         self.join(timeout=5)
-        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
-        reasons = []
-        for name, col in (("hw_slowdown", 3), ("hw_thermal_slowdown", 4), ("sw_thermal_slowdown", 5), ("sw_power_cap", 6)):
-            if any(len(r) > col and r[col].lower().startswith("active") for r in self.rows):
-                reasons.append(name)
-        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None, reasons=reasons, samples=len(self.rows))
+        names = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+        reasons = [n for bit, n in names.items() if self.bits & bit]
+        return dict(sm_mhz=float(np.median(self.sm)) if self.sm else None, sm_max_mhz=self.mx, reasons=reasons, samples=len(self.sm))
+
+
+def combine_results(dist, world, src, gathered, out, sum_count, header):
+    """ONE collective per sampling interval: all-gather of the per-GPU result vectors (2.6 KB each), then SUM / MAX locally
+    (include/lokib200.h: entries [SUM_COUNT, HEADER) combine with max, all others with sum).  Leaves the combined vector in `out`."""
+    import torch
+    L = out.numel()
+    if world > 1:
+        dist.all_gather_into_tensor(gathered, src)
+        g2 = gathered.view(world, L)
+        torch.sum(g2, dim=0, out=out)
+        out[sum_count:header] = g2[:, sum_count:header].max(dim=0).values
+    elif src is not out:
+        out.copy_(src)
+    return out
 
 
 def measured_hbm_peak():
@@ -151,13 +165,13 @@ def run_reference_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--model", default="n2_aniso")
     ap.add_argument("--electrons", type=float, default=1e7, help="electrons per GPU")
     ap.add_argument("--relax", type=int, default=60, help="untimed relaxation intervals before the warm-up")
-    ap.add_argument("--ref-electrons", type=int, default=50_000)
+    ap.add_argument("--ref-electrons", type=int, default=200_000)
     ap.add_argument("--ref-points", type=int, default=500)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -193,22 +207,18 @@ def main():
     nu = eng.check_nu_trial(mx, eng.table_info()["nu_max_last"], horizon=11.0)
 
     d_res = torch.zeros(L, dtype=torch.float64, device="cuda")
-    d_max = torch.zeros(2, dtype=torch.float64, device="cuda")
+    d_buf = [torch.zeros(L, dtype=torch.float64, device="cuda") for _ in range(2)]
+    d_gather = torch.zeros(world * L, dtype=torch.float64, device="cuda")
     d_events = torch.zeros(1, dtype=torch.float64, device="cuda")
+    comm_stream = torch.cuda.Stream()
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def allreduce_result():
-        # one NCCL all-reduce per sampling interval: SUM part and MAX part of the result vector (include/lokib200.h)
-        if world > 1:
-            d_max.copy_(d_res[R.SUM_COUNT:R.HEADER])
-            d_res[R.SUM_COUNT:R.HEADER] = 0
-            dist.all_reduce(d_res, op=dist.ReduceOp.SUM)
-            dist.all_reduce(d_max, op=dist.ReduceOp.MAX)
-            d_res[R.SUM_COUNT:R.HEADER] = d_max
+    def combine(src):
+        return combine_results(dist, world, src, d_gather, d_res, R.SUM_COUNT, R.HEADER)
 
     def host_step(t):
         """the blocking C-ABI call with the host-side trial-frequency logic a driver runs every interval"""
@@ -217,7 +227,7 @@ def main():
         t += 1.0 / nu
         res = eng.advance(nu, t, sample=True)
         if world > 1:
-            d_res.copy_(torch.from_numpy(res)); allreduce_result(); res = d_res.cpu().numpy()
+            d_buf[0].copy_(torch.from_numpy(res)); combine(d_buf[0]); res = d_res.cpu().numpy()
         mx = max(res[R.MAX_EPS], res[R.MAX_EPS_SEEN])
         return t, res
 
@@ -247,11 +257,20 @@ def main():
     d_events.zero_()
     barrier()
     e0.record()
-    for _ in range(args.steps):
+    free_evt = [None, None]
+    for i in range(args.steps):
         t += 1.0 / nu
-        eng.advance_device(nu, t, True, d_res.data_ptr())
-        allreduce_result()
-        d_events += d_res[R.N_REAL] + d_res[R.N_NULL]
+        buf = d_buf[i & 1]
+        if free_evt[i & 1] is not None:
+            stream.wait_event(free_evt[i & 1])          # the collective that read this buffer two steps ago is done
+        eng.advance_device(nu, t, True, buf.data_ptr())
+        ready = torch.cuda.Event(); ready.record(stream)
+        with torch.cuda.stream(comm_stream):            # combine on a side stream: overlaps with the next interval's kernels
+            comm_stream.wait_event(ready)
+            combine(buf)
+            d_events.add_(d_res[R.N_REAL] + d_res[R.N_NULL])
+            free_evt[i & 1] = torch.cuda.Event(); free_evt[i & 1].record(comm_stream)
+    stream.wait_stream(comm_stream)
     e1.record()
     barrier()
     ms_dev = e0.elapsed_time(e1)
@@ -267,6 +286,13 @@ def main():
     final = d_res.cpu().numpy()
     if rank == 0:
         peak, peak_src = measured_hbm_peak()
+        traffic = None
+        try:   # DRAM bytes of one K1 launch from the committed ncu --set full capture (same workload only)
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+            if tj["electrons"] == n and args.model == "n2_aniso":
+                traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
+        except Exception:
+            pass
         ev_per_launch_rank = ev_dev / world / args.steps
         achieved = STATE_BYTES_PER_EVENT * ev_per_launch_rank / (adv_ms * 1e-3) / 1e9 if adv_ms > 0 else None
         line = dict(
@@ -279,7 +305,7 @@ def main():
             e2e=dict(value=ev_e2e / (ms_e2e * 1e-3), unit="events/s", h2d_bytes_per_step=16 * world,
                      d2h_bytes_per_step=8 * L * world, ms_per_step=ms_e2e / args.steps),
             gpu_launches=int(launches * world), clocks=clocks,
-            roofline=dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=(achieved / peak) if achieved else None, traffic=None,
+            roofline=dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=(achieved / peak) if achieved else None, traffic=traffic,
                           kernel="k_advance", kernel_ms=adv_ms, kernel_launches=adv_n, bytes_per_event=STATE_BYTES_PER_EVENT, peak_source=peak_src,
                           kernel_share_of_step=adv_ms * adv_n / ms_dev if ms_dev > 0 else None))
         if world == 1 and not args.no_cpu_baseline:
