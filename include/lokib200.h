@@ -248,6 +248,10 @@ int lokib200_job_histograms(lokib200_job* j, double* eeh, double* eah, double* e
 /* phase-resolved sums (AC field): nIntegrationPointsPerPhase[nPh], meanEnergies_periodic[nPh], fluxVelocities_periodic[nPh][3],
  * bulkVelocities_periodic[nPh][3] (already divided by the points per phase, BMC.C:1728-1734) */
 int lokib200_job_periodic(const lokib200_job* j, double* points_per_phase, double* mean_energy, double* flux_velocity, double* bulk_velocity);
+/* fluxDiffusionCoeffs_periodic[nPh][9], bulkDiffusionCoeffs_periodic[nPh][9] (BMC.C:1479-1480, divided by the points per phase) */
+int lokib200_job_periodic_diffusion(const lokib200_job* j, double* flux_diffusion, double* bulk_diffusion);
+/* job constants: the summed-over-engines configuration (n_electrons = all shards) and the number of processes */
+int lokib200_job_conditions(const lokib200_job* j, lokib200_config* cfg, int32_t* n_processes);
 const char* lokib200_job_last_error(const lokib200_job* j);
 void lokib200_job_destroy(lokib200_job* j);
 

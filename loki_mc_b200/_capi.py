@@ -32,16 +32,37 @@ def lib_path():
     return os.environ.get("LOKIB200_LIB") or os.path.join(PKG, "liblokib200.so")
 
 
+HOST_SOURCES = ("boltzmann_mc.cpp", "setup_input.cpp", "host_capi.cpp")
+HOST_HEADERS = ("setup_input.h",)
+
+
+def _stale(out, deps):
+    return not os.path.exists(out) or any(os.path.getmtime(out) < os.path.getmtime(d) for d in deps)
+
+
 def build(force=False, verbose=False):
-    """Compile csrc/lokib200.cu for sm_100a into loki_mc_b200/liblokib200.so (in-tree, so it travels to the GPU box)."""
+    """Compile the CUDA engine (csrc/lokib200.cu, sm_100a) and the host sources into loki_mc_b200/liblokib200.so (in-tree, so it
+    travels to the GPU box).  Objects are cached under loki_mc_b200/build/ and rebuilt when a source or header is newer."""
     out = lib_path()
-    srcs = [os.path.join(SRC, "lokib200.cu"), os.path.join(PKG, "host", "boltzmann_mc.cpp")] + \
-           [os.path.join(SRC, f) for f in ("lk_stream.cuh", "lk_tile.cuh", "lk_kernels.cuh", "lk_physics.cuh")] + [os.path.join(ROOT, "include", "lokib200.h")]
-    if not force and os.path.exists(out) and all(os.path.getmtime(out) >= os.path.getmtime(s) for s in srcs):
-        return out
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", out, srcs[0], srcs[1]]
-    subprocess.check_call(cmd)
+    objdir = os.path.join(PKG, "build")
+    os.makedirs(objdir, exist_ok=True)
+    public = [os.path.join(ROOT, "include", f) for f in ("lokib200.h", "lokib200_host.h")]
+    cu = os.path.join(SRC, "lokib200.cu")
+    cu_deps = [cu] + [os.path.join(SRC, f) for f in ("lk_stream.cuh", "lk_tile.cuh", "lk_kernels.cuh", "lk_physics.cuh")] + public
+    host_deps = [os.path.join(PKG, "host", f) for f in HOST_HEADERS] + public
+    compile_flags = [f for f in NVCC_FLAGS if f != "-shared"]
+    objs = []
+    jobs = [(cu, os.path.join(objdir, "lokib200.o"), cu_deps)] + \
+           [(os.path.join(PKG, "host", f), os.path.join(objdir, f[:-4] + ".o"), [os.path.join(PKG, "host", f)] + host_deps) for f in HOST_SOURCES]
+    relinked = False
+    for src, obj, deps in jobs:
+        if force or _stale(obj, deps):
+            subprocess.check_call([nvcc] + compile_flags + (["-Xptxas", "-v"] if verbose and src == cu else []) + ["-c", "-o", obj, src])
+            relinked = True
+        objs.append(obj)
+    if relinked or _stale(out, objs):
+        subprocess.check_call([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", out] + objs)
     return out
 
 
@@ -104,7 +125,13 @@ SYMBOLS = ["lokib200_abi_version", "lokib200_device_count", "lokib200_create", "
            "lokib200_launch_count", "lokib200_kernel_time_ms", "lokib200_get_config", "lokib200_process_count", "lokib200_get_rel_densities",
            "lokib200_sample_moments", "lokib200_regrid_energy_histograms", "lokib200_read_result", "lokib200_job_create", "lokib200_job_solve",
            "lokib200_job_process_outputs", "lokib200_job_time_series", "lokib200_job_histograms", "lokib200_job_periodic",
-           "lokib200_job_last_error", "lokib200_job_destroy"]
+           "lokib200_job_periodic_diffusion", "lokib200_job_conditions", "lokib200_job_last_error", "lokib200_job_destroy"]
+# every symbol include/lokib200_host.h declares
+HOST_SYMBOLS = ["lokib200_setup_load", "lokib200_setup_destroy", "lokib200_setup_last_error", "lokib200_setup_job_count", "lokib200_setup_job_value",
+                "lokib200_setup_variable_condition", "lokib200_setup_processes", "lokib200_setup_config", "lokib200_setup_controls",
+                "lokib200_setup_process_description", "lokib200_setup_process_is_elastic", "lokib200_setup_energy_max_elastic",
+                "lokib200_setup_value", "lokib200_setup_dump", "lokib200_setup_warning_count", "lokib200_setup_warning",
+                "lokib200_eval_expression", "lokib200_eval_vector_expression"]
 
 
 def lib():
@@ -152,10 +179,35 @@ def lib():
     L.lokib200_job_time_series.argtypes = [vp, c_dp, c_dp, c_dp, c_dp, c_dp]; L.lokib200_job_time_series.restype = C.c_int64
     L.lokib200_job_histograms.argtypes = [vp, c_dp, c_dp, c_dp, c_dp]
     L.lokib200_job_periodic.argtypes = [vp, c_dp, c_dp, c_dp, c_dp]
+    L.lokib200_job_periodic_diffusion.argtypes = [vp, c_dp, c_dp]
+    L.lokib200_job_conditions.argtypes = [vp, C.POINTER(Config), c_ip]
     L.lokib200_job_last_error.argtypes = [vp]; L.lokib200_job_last_error.restype = C.c_char_p
     L.lokib200_job_destroy.argtypes = [vp]; L.lokib200_job_destroy.restype = None
+    _bind_host(L)
     _LIB = L
     return L
+
+
+def _bind_host(L):
+    vp = C.c_void_p
+    L.lokib200_setup_load.argtypes = [C.c_char_p, C.c_char_p, C.POINTER(vp)]
+    L.lokib200_setup_destroy.argtypes = [vp]; L.lokib200_setup_destroy.restype = None
+    L.lokib200_setup_last_error.argtypes = [vp]; L.lokib200_setup_last_error.restype = C.c_char_p
+    L.lokib200_setup_job_count.argtypes = [vp]
+    L.lokib200_setup_job_value.argtypes = [vp, C.c_int32]; L.lokib200_setup_job_value.restype = C.c_double
+    L.lokib200_setup_variable_condition.argtypes = [vp]; L.lokib200_setup_variable_condition.restype = C.c_char_p
+    L.lokib200_setup_processes.argtypes = [vp, C.POINTER(ProcessSoA)]
+    L.lokib200_setup_config.argtypes = [vp, C.c_int32, C.POINTER(Config)]
+    L.lokib200_setup_controls.argtypes = [vp, C.POINTER(SolveControls)]
+    L.lokib200_setup_process_description.argtypes = [vp, C.c_int32]; L.lokib200_setup_process_description.restype = C.c_char_p
+    L.lokib200_setup_process_is_elastic.argtypes = [vp, C.c_int32]
+    L.lokib200_setup_energy_max_elastic.argtypes = [vp]; L.lokib200_setup_energy_max_elastic.restype = C.c_double
+    L.lokib200_setup_value.argtypes = [vp, C.c_char_p]; L.lokib200_setup_value.restype = C.c_char_p
+    L.lokib200_setup_dump.argtypes = [vp, C.c_char_p, C.c_int64]; L.lokib200_setup_dump.restype = C.c_int64
+    L.lokib200_setup_warning_count.argtypes = [vp]
+    L.lokib200_setup_warning.argtypes = [vp, C.c_int32]; L.lokib200_setup_warning.restype = C.c_char_p
+    L.lokib200_eval_expression.argtypes = [C.c_char_p, c_ip]; L.lokib200_eval_expression.restype = C.c_double
+    L.lokib200_eval_vector_expression.argtypes = [C.c_char_p, c_dp, C.c_int64, c_ip]; L.lokib200_eval_vector_expression.restype = C.c_int64
 
 
 def _dp(a):
@@ -374,3 +426,97 @@ class Job:
             self.close()
         except Exception:
             pass
+
+
+class Setup:
+    """A parsed LoKI-MC setup file (include/lokib200_host.h): flattened process set + per-job engine configuration.
+    Host-only; works without a GPU."""
+
+    def __init__(self, input_dir, setup_file):
+        L = lib()
+        self.L = L
+        h = C.c_void_p()
+        rc = L.lokib200_setup_load(os.fsencode(input_dir), os.fsencode(setup_file), C.byref(h))
+        if rc != 0:
+            raise LokiB200Error(L.lokib200_setup_last_error(None).decode())
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.lokib200_setup_destroy(self.h); self.h = None
+
+    __del__ = close
+
+    @property
+    def n_jobs(self):
+        return int(self.L.lokib200_setup_job_count(self.h))
+
+    def job_value(self, job):
+        return float(self.L.lokib200_setup_job_value(self.h, job))
+
+    @property
+    def variable_condition(self):
+        return self.L.lokib200_setup_variable_condition(self.h).decode()
+
+    def value(self, key):
+        return self.L.lokib200_setup_value(self.h, key.encode()).decode()
+
+    def dump(self):
+        n = self.L.lokib200_setup_dump(self.h, None, 0)
+        buf = C.create_string_buffer(n + 1)
+        self.L.lokib200_setup_dump(self.h, buf, n + 1)
+        return buf.value.decode()
+
+    @property
+    def warnings(self):
+        return [self.L.lokib200_setup_warning(self.h, i).decode() for i in range(self.L.lokib200_setup_warning_count(self.h))]
+
+    def config(self, job=0):
+        cfg = Config()
+        if self.L.lokib200_setup_config(self.h, job, C.byref(cfg)) != 0:
+            raise LokiB200Error(self.L.lokib200_setup_last_error(self.h).decode())
+        return cfg
+
+    def controls(self):
+        c = SolveControls()
+        if self.L.lokib200_setup_controls(self.h, C.byref(c)) != 0:
+            raise LokiB200Error(self.L.lokib200_setup_last_error(self.h).decode())
+        return c
+
+    def processes(self):
+        """the flattened process set as the dict layout of tests/golden_io (copies)"""
+        p = ProcessSoA()
+        self.L.lokib200_setup_processes(self.h, C.byref(p))
+        P, G = p.n_processes, p.n_gases
+        def arr(ptr, n):
+            return np.ctypeslib.as_array(ptr, shape=(n,)).copy()
+        off = arr(p.xs_offset, P + 1)
+        d = {"p_type": arr(p.type, P), "p_superelastic": arr(p.is_superelastic, P), "p_angular": arr(p.angular_model, P),
+             "p_ap0": arr(p.angular_p0, P), "p_ap1": arr(p.angular_p1, P), "p_swf": arr(p.superelastic_weight_factor, P),
+             "p_emin": arr(p.energy_min, P), "p_emax": arr(p.energy_max, P), "p_reldens": arr(p.rel_density, P), "p_mass": arr(p.target_mass, P),
+             "p_redmass": arr(p.reduced_mass, P), "p_eloss": arr(p.energy_loss, P), "p_thstd": arr(p.thermal_std, P), "p_w": arr(p.w_parameter, P),
+             "gas_first": arr(p.gas_first, G), "gas_last": arr(p.gas_last, G), "gas_fraction": arr(p.gas_fraction, G), "xs_offset": off,
+             "xs_energy": arr(p.xs_energy, int(off[-1])), "xs_value": arr(p.xs_value, int(off[-1]))}
+        d["p_elastic"] = np.array([self.L.lokib200_setup_process_is_elastic(self.h, k) for k in range(P)], dtype=np.int32)
+        d["descriptions"] = [self.L.lokib200_setup_process_description(self.h, k).decode() for k in range(P)]
+        d["energy_max_elastic"] = float(self.L.lokib200_setup_energy_max_elastic(self.h))
+        return d
+
+
+def eval_expression(expr):
+    ok = C.c_int32(0)
+    v = lib().lokib200_eval_expression(expr.encode(), C.byref(ok))
+    if not ok.value:
+        raise LokiB200Error(lib().lokib200_setup_last_error(None).decode())
+    return float(v)
+
+
+def eval_vector_expression(expr):
+    ok = C.c_int32(0)
+    L = lib()
+    n = L.lokib200_eval_vector_expression(expr.encode(), None, 0, C.byref(ok))
+    if not ok.value:
+        raise LokiB200Error(L.lokib200_setup_last_error(None).decode())
+    out = np.zeros(max(int(n), 1))
+    L.lokib200_eval_vector_expression(expr.encode(), _dp(out), n, C.byref(ok))
+    return out[:n]

@@ -81,6 +81,7 @@ struct lokib200_job {
   double integrationPhaseStep = 0;
   std::vector<double> nIntegrationPointsPerPhase, meanEnergies_periodic;
   std::vector<Vec3> fluxVelocities_periodic, bulkVelocities_periodic;
+  std::vector<Mat9> fluxDiffusionCoeffs_periodic, bulkDiffusionCoeffs_periodic;
   // histogram carry of earlier energy grids (BMC.C:1497-1548) and final sums
   bool histGridSet = false;
   std::vector<double> carryEeh, carryEah, carryEehPeriodic;
@@ -183,6 +184,7 @@ struct lokib200_job {
       const int ph = phaseIndex();
       nIntegrationPointsPerPhase[ph] += 1.0; meanEnergies_periodic[ph] += me;
       for (int a = 0; a < 3; ++a) { fluxVelocities_periodic[ph][a] += mv[a]; bulkVelocities_periodic[ph][a] += bv[a]; }
+      for (int a = 0; a < 9; ++a) { fluxDiffusionCoeffs_periodic[ph][a] += fd[a]; bulkDiffusionCoeffs_periodic[ph][a] += bd[a]; }
     }
     return 0;
   }
@@ -381,6 +383,7 @@ struct lokib200_job {
         const double c = nIntegrationPointsPerPhase[p];
         meanEnergies_periodic[p] /= c;
         for (int a = 0; a < 3; ++a) { fluxVelocities_periodic[p][a] /= c; bulkVelocities_periodic[p][a] /= c; }
+        for (int a = 0; a < 9; ++a) { fluxDiffusionCoeffs_periodic[p][a] /= c; bulkDiffusionCoeffs_periodic[p][a] /= c; }
       }
     }
     checkStatisticalErrors();                                                          // :418
@@ -420,6 +423,7 @@ int lokib200_job_create(lokib200_engine* const* engines, int32_t n_engines, cons
   j->integrationPhaseStep = TWO_PI / j->nPhases;                                        // BMC.C:525
   j->nIntegrationPointsPerPhase.assign(j->nPhases, 0.0); j->meanEnergies_periodic.assign(j->nPhases, 0.0);
   j->fluxVelocities_periodic.assign(j->nPhases, Vec3{}); j->bulkVelocities_periodic.assign(j->nPhases, Vec3{});
+  j->fluxDiffusionCoeffs_periodic.assign(j->nPhases, Mat9{}); j->bulkDiffusionCoeffs_periodic.assign(j->nPhases, Mat9{});
   j->carryEeh.assign(j->cfg.n_energy_cells, 0.0);
   j->carryEah.assign(static_cast<size_t>(j->cfg.n_energy_cells) * j->cfg.n_cos_cells, 0.0);
   j->carryEehPeriodic.assign(static_cast<size_t>(j->nPhases) * j->cfg.n_energy_cells, 0.0);
@@ -488,6 +492,22 @@ int lokib200_job_periodic(const lokib200_job* j, double* pts, double* me, double
     if (fv) for (int a = 0; a < 3; ++a) fv[3 * p + a] = j->fluxVelocities_periodic[p][a];
     if (bv) for (int a = 0; a < 3; ++a) bv[3 * p + a] = j->bulkVelocities_periodic[p][a];
   }
+  return 0;
+}
+
+int lokib200_job_periodic_diffusion(const lokib200_job* j, double* fd, double* bd) {
+  if (!j) return LOKIB200_ERR_INVALID;
+  for (int p = 0; p < j->nPhases; ++p) for (int a = 0; a < 9; ++a) {
+    if (fd) fd[9 * p + a] = j->fluxDiffusionCoeffs_periodic[p][a];
+    if (bd) bd[9 * p + a] = j->bulkDiffusionCoeffs_periodic[p][a];
+  }
+  return 0;
+}
+
+int lokib200_job_conditions(const lokib200_job* j, lokib200_config* cfg, int32_t* n_processes) {
+  if (!j) return LOKIB200_ERR_INVALID;
+  if (cfg) { *cfg = j->cfg; cfg->n_electrons = static_cast<int64_t>(j->nElectrons); }
+  if (n_processes) *n_processes = j->P;
   return 0;
 }
 

@@ -13,6 +13,10 @@
 //                                  trialCollisionFrequency = maxCollisionFrequencies[nE-1] (BoltzmannMC.C:515)
 //   event <nu_trial> <t_e> <x y z> <vx vy vz> <t_cf|ND> <nu_e> <t_sync> <n> <d0..dn-1>
 //                               -> one pass of the per-electron loop body, BoltzmannMC.C:637-681, on electron 0
+//   expr <text> / vexpr <text>  -> Parse::str2value / Parse::evalVectorExpress (Parse.C:610-755)
+//   controls                    -> the numericsMC keys as stored by the BoltzmannMC constructor
+//   solve <seed>                -> runs every job of the setup (BoltzmannMC::solve, Setup::nextJob) on a deterministic generator; dumps the raw
+//                                  state the sinks read (<prefix>.job<k>.raw.bin) and lets the reference's Output write its files
 //   maxaccel <eps> <dt>         -> maximizationAccelerationEnergy (BoltzmannMC.C:765-802)
 //   moments <file.bin>          -> calculateMeanDataForSwarmParams (BoltzmannMC.C:1410-1482) on N=(nElectrons) electrons
 //                                  read from file (x[N] y[N] z[N] vx[N] vy[N] vz[N] doubles)
@@ -39,11 +43,16 @@
 
 static std::deque<double> g_draws;
 static long g_used = 0;
+static unsigned long long g_prng = 0;
 
 // interposes the library's definition
 double MathFunctions::unitUniformRand(bool includeZero, bool includeOne) {
   (void)includeZero; (void)includeOne;
   ++g_used;
+  if (g_draws.empty() && g_prng) {   // 'solve': a deterministic generator (xorshift64*), open interval
+    g_prng ^= g_prng >> 12; g_prng ^= g_prng << 25; g_prng ^= g_prng >> 27;
+    return ((double)((g_prng * 0x2545F4914F6CDD1DULL) >> 11) + 0.5) * (1.0 / 9007199254740992.0);
+  }
   if (g_draws.empty()) return 0.5;
   double d = g_draws.front();
   g_draws.pop_front();
@@ -165,6 +174,65 @@ int main(int argc, char** argv) {
                    ek->ejectedElectronPositions(id, 0), ek->ejectedElectronPositions(id, 1), ek->ejectedElectronPositions(id, 2),
                    ek->ejectedElectronVelocities(id, 0), ek->ejectedElectronVelocities(id, 1), ek->ejectedElectronVelocities(id, 2),
                    ek->ejectedElectronEnergies[id], g_used);
+    }
+    else if (cmd == "expr" || cmd == "vexpr") {   // Parse::str2value / evalVectorExpress on the rest of the line
+      std::string rest; std::getline(is, rest);
+      rest.erase(0, rest.find_first_not_of(' '));
+      if (cmd == "expr") std::fprintf(out, "expr %.17g\n", Parse::str2value(rest));
+      else { std::fprintf(out, "vexpr"); for (double v : Parse::evalVectorExpress(rest)) std::fprintf(out, " %.17g", v); std::fprintf(out, "\n"); }
+    }
+    else if (cmd == "controls") {   // numericsMC keys as the BoltzmannMC ctor stores them (BoltzmannMC.h:262-365)
+      std::fprintf(out, "controls %.17g %.17g %.17g %d %d %.17g %.17g %.17g %.17g %.17g %.17g %.17g %.17g %.17g %.17g %.17g %d %d %d %d %d %d %.17g\n",
+                   ek->requiredIntegrationPoints, ek->requiredIntegratedSSTimes, ek->requiredIntegratedAbsoluteTime, (int)ek->errorsToBeChecked,
+                   ek->synchronizationOverSampling, ek->requiredMeanEnergyRelError, ek->requiredFluxDriftVelocityRelError,
+                   ek->requiredFluxDiffusionCoeffsRelError, ek->requiredBulkDriftVelocityRelError, ek->requiredBulkDiffusionCoeffsRelError,
+                   ek->requiredPowerBalanceRelError, ek->minCollisionsBeforeSteadyState, ek->maxCollisionsBeforeSteadyState,
+                   ek->maxCollisionsAfterSteadyState, ek->synchronizationTimeXMaxCollisionFrequency, ek->initialElecTempOverGasTemp,
+                   (int)ek->nEnergyCells, (int)ek->nCosAngleCells, (int)ek->nRadialVelocityCells, (int)ek->nAxialVelocityCells,
+                   (int)ek->nIntegrationPhases, (int)ek->interpolCrossSectionSize, (double)ek->nElectrons);
+    }
+    else if (cmd == "solve") {   // full jobs with a deterministic generator; raw BoltzmannMC state -> <prefix>.job<k>.raw.bin, files via Output
+      unsigned long long seed; is >> seed;
+      for (int job = 0; setup.currentJobID < setup.numberOfJobs; ++job) {
+        g_prng = seed + 0x9E3779B97F4A7C15ULL * (unsigned long long)(job + 1);
+        g_draws.clear();
+        ek->solve();
+        FILE* f = std::fopen((prefix + ".job" + std::to_string(job) + ".raw.bin").c_str(), "wb");
+        auto put = [&](double v) { std::fwrite(&v, sizeof(double), 1, f); };
+        auto putv = [&](const Eigen::ArrayXd& a) { for (int i = 0; i < a.size(); ++i) put(a[i]); };
+        auto putm = [&](const Eigen::ArrayXXd& a, int rows) { for (int i = 0; i < rows; ++i) for (int c = 0; c < a.cols(); ++c) put(a(i, c)); };
+        auto putm3 = [&](const Eigen::Matrix3d& a) { for (int i = 0; i < 3; ++i) for (int c = 0; c < 3; ++c) put(a(i, c)); };
+        const bool ac = ek->excitationFrequencyRadians != 0;
+        const int nS = ek->nSamplingPoints, nPh = ac ? ek->nIntegrationPhases : 0;
+        put(P); put(ek->nEnergyCells); put(ek->nCosAngleCells); put(ek->nRadialVelocityCells); put(ek->nAxialVelocityCells); put(nPh); put(nS);
+        put(ek->isCylindricallySymmetric); put(ek->nElectrons);
+        put(ek->averagedMeanEnergy); put(ek->averagedMeanEnergyError);
+        putv(ek->averagedFluxDriftVelocity); putv(ek->averagedFluxDriftVelocityError); putm3(ek->averagedFluxDiffusionCoeffs); putm3(ek->averagedFluxDiffusionCoeffsError);
+        putv(ek->averagedBulkDriftVelocity); putv(ek->averagedBulkDriftVelocityError); putm3(ek->averagedBulkDiffusionCoeffs); putm3(ek->averagedBulkDiffusionCoeffsError);
+        put(ek->averagedPowerGainField); put(ek->averagedPowerGrowth); put(ek->powerBalanceRelError);
+        put(ek->time); put(ek->steadyStateTime); put(ek->totalIntegratedTime); put(ek->trialCollisionFrequency); put(ek->maxEedfEnergy); put(ek->elapsedTime);
+        put((double)ek->totalCollisionCounter); put((double)ek->nullCollisionCounter); put((double)ek->collisionCounterAtSS); put((double)ek->nullCollisionCounterAtSS);
+        put(ek->nSamplingPoints); put(ek->nIntegrationPoints);
+        put(ek->radialVelocityNodes[ek->nRadialVelocityCells]);   // maxSpeed of the velocity grid (fixed at steady state)
+        for (int k = 0; k < P; ++k) put(ek->averagedRateCoeffs[k]);
+        for (int k = 0; k < P; ++k) put(ek->averagedPowerGainProcesses[k]);
+        for (int k = 0; k < P; ++k) put(ek->averagedPowerLossProcesses[k]);
+        for (int k = 0; k < P; ++k) put((double)ek->collisionCounters[k]);
+        putv(ek->eehSum);
+        if (ek->isCylindricallySymmetric) { putm(ek->eahSum, ek->nEnergyCells); putm(ek->evhSum, ek->nRadialVelocityCells); }
+        if (ac) putm(ek->eehSum_periodic, nPh);
+        for (int i = 0; i < nS; ++i) put(ek->samplingTimes[i]);
+        for (int i = 0; i < nS; ++i) put(ek->meanEnergies[i]);
+        putm(ek->meanPositions, nS); putm(ek->meanVelocities, nS); putm(ek->positionCovariances, nS);
+        if (ac) {
+          putv(ek->nIntegrationPointsPerPhase); putv(ek->meanEnergies_periodic); putm(ek->fluxVelocities_periodic, nPh); putm(ek->bulkVelocities_periodic, nPh);
+          putm(ek->fluxDiffusionCoeffs_periodic, nPh); putm(ek->bulkDiffusionCoeffs_periodic, nPh);
+        }
+        std::fclose(f);
+        std::fprintf(out, "solve job %d meanEnergy %.17g samples %d\n", job, ek->averagedMeanEnergy, nS);
+        setup.nextJob();
+      }
+      setup.finishSimulation();
     }
     else if (cmd == "maxaccel") {
       double e0, dt; is >> e0 >> dt;

@@ -12,16 +12,17 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def test_library_exports_every_declared_symbol():
     import loki_mc_b200 as lk
-    from loki_mc_b200._capi import SYMBOLS
+    from loki_mc_b200._capi import HOST_SYMBOLS, SYMBOLS
     if not os.path.exists(lk.lib_path()):
         lk.build()
     L = lk.lib()
-    hdr = open(os.path.join(ROOT, "include", "lokib200.h")).read()
-    declared = sorted(set(re.findall(r"\b(lokib200_[a-z0-9_]+)\s*\(", hdr)))
-    assert declared, "no declarations found"
-    for s in declared:
-        assert hasattr(L, s), "missing symbol " + s
-    assert sorted(SYMBOLS) == declared
+    for header, symbols in (("lokib200.h", SYMBOLS), ("lokib200_host.h", HOST_SYMBOLS)):
+        hdr = open(os.path.join(ROOT, "include", header)).read()
+        declared = sorted(set(re.findall(r"\b(lokib200_[a-z0-9_]+)\s*\(", hdr)))
+        assert declared, "no declarations found in " + header
+        for s in declared:
+            assert hasattr(L, s), "missing symbol " + s
+        assert sorted(symbols) == declared, header
     assert L.lokib200_abi_version() == 1
 
 
