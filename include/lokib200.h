@@ -239,6 +239,8 @@ typedef struct lokib200_solve_results {   /* the public members the reference's 
 typedef struct lokib200_job lokib200_job;
 int lokib200_job_create(lokib200_engine* const* engines, int32_t n_engines, const lokib200_solve_controls* c, lokib200_job** out);
 int lokib200_job_solve(lokib200_job* j, lokib200_solve_results* res);
+/* the results of the last successful lokib200_job_solve (error if the job has not been solved) */
+int lokib200_job_results(const lokib200_job* j, lokib200_solve_results* res);
 /* per-process outputs: averagedRateCoeffs, averagedPowerGainProcesses, averagedPowerLossProcesses, collisionCounters (after steady state) */
 int lokib200_job_process_outputs(const lokib200_job* j, double* rate_coeffs, double* power_gain, double* power_loss, double* counts);
 /* time series (MCTemporalInfo): sampling times, mean energies, mean positions[3], mean velocities[3], position covariances[9] per sample; any may be NULL */
@@ -250,6 +252,8 @@ int lokib200_job_histograms(lokib200_job* j, double* eeh, double* eah, double* e
 int lokib200_job_periodic(const lokib200_job* j, double* points_per_phase, double* mean_energy, double* flux_velocity, double* bulk_velocity);
 /* fluxDiffusionCoeffs_periodic[nPh][9], bulkDiffusionCoeffs_periodic[nPh][9] (BMC.C:1479-1480, divided by the points per phase) */
 int lokib200_job_periodic_diffusion(const lokib200_job* j, double* flux_diffusion, double* bulk_diffusion);
+/* upper node of the velocity-histogram grids, sqrt(2 e maxEedfEnergy / m) at the moment the steady state was found (BMC.C:1877-1884) */
+double lokib200_job_evdf_max_speed(const lokib200_job* j);
 /* job constants: the summed-over-engines configuration (n_electrons = all shards) and the number of processes */
 int lokib200_job_conditions(const lokib200_job* j, lokib200_config* cfg, int32_t* n_processes);
 const char* lokib200_job_last_error(const lokib200_job* j);

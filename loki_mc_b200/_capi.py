@@ -32,8 +32,8 @@ def lib_path():
     return os.environ.get("LOKIB200_LIB") or os.path.join(PKG, "liblokib200.so")
 
 
-HOST_SOURCES = ("boltzmann_mc.cpp", "setup_input.cpp", "host_capi.cpp")
-HOST_HEADERS = ("setup_input.h",)
+HOST_SOURCES = ("boltzmann_mc.cpp", "setup_input.cpp", "report.cpp", "host_capi.cpp", "run.cpp")
+HOST_HEADERS = ("setup_input.h", "report.h")
 
 
 def _stale(out, deps):
@@ -63,6 +63,9 @@ def build(force=False, verbose=False):
         objs.append(obj)
     if relinked or _stale(out, objs):
         subprocess.check_call([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", out] + objs)
+    exe, main_src = os.path.join(PKG, "lokimc_b200"), os.path.join(PKG, "host", "lokimc_main.cpp")
+    if out == os.path.join(PKG, "liblokib200.so") and (force or _stale(exe, [main_src, out] + public)):   # the command-line front end
+        subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-o", exe, main_src, "-L" + PKG, "-llokib200", "-Wl,-rpath,$ORIGIN"])
     return out
 
 
@@ -111,6 +114,20 @@ class SolveResults(C.Structure):
                 ("good_statistical_errors", C.c_int32), ("stopped_by_max_collisions", C.c_int32)]
 
 
+class JobData(C.Structure):
+    _fields_ = [("results", C.POINTER(SolveResults)), ("n_electrons", C.c_double), ("evdf_max_speed", C.c_double),
+                ("rate_coeffs", c_dp), ("power_gain", c_dp), ("power_loss", c_dp), ("counts", c_dp),
+                ("eeh", c_dp), ("eah", c_dp), ("evh", c_dp), ("eeh_periodic", c_dp), ("n_samples", C.c_int64),
+                ("times", c_dp), ("mean_energy", c_dp), ("mean_pos", c_dp), ("mean_vel", c_dp), ("pos_cov", c_dp),
+                ("points_per_phase", c_dp), ("mean_energy_periodic", c_dp), ("flux_velocity_periodic", c_dp), ("bulk_velocity_periodic", c_dp),
+                ("flux_diffusion_periodic", c_dp), ("bulk_diffusion_periodic", c_dp)]
+
+
+class RunSummary(C.Structure):
+    _fields_ = [("n_jobs", C.c_int32), ("last_mean_energy", C.c_double), ("total_collisions", C.c_double), ("device_seconds", C.c_double),
+                ("elapsed_seconds", C.c_double)]
+
+
 ELECTRON_DTYPE = np.dtype([("r", "f8", 3), ("v", "f8", 3), ("energy", "f8"), ("t", "f8"), ("t_cf", "f8"), ("nu_e", "f8")])
 EVENT_DTYPE = np.dtype([("chosen", "i4"), ("draws_used", "i4"), ("dE", "f8"), ("dE_rel", "f8"), ("gain_field", "f8"), ("ej_r", "f8", 3),
                         ("ej_v", "f8", 3), ("ej_energy", "f8")])
@@ -123,15 +140,18 @@ SYMBOLS = ["lokib200_abi_version", "lokib200_device_count", "lokib200_create", "
            "lokib200_advance_to_sync", "lokib200_advance_to_sync_device", "lokib200_set_histogram_grid", "lokib200_sample_histograms",
            "lokib200_fetch_histograms", "lokib200_step_injected", "lokib200_max_accel_energy", "lokib200_check_nu_trial",
            "lokib200_launch_count", "lokib200_kernel_time_ms", "lokib200_get_config", "lokib200_process_count", "lokib200_get_rel_densities",
-           "lokib200_sample_moments", "lokib200_regrid_energy_histograms", "lokib200_read_result", "lokib200_job_create", "lokib200_job_solve",
+           "lokib200_sample_moments", "lokib200_regrid_energy_histograms", "lokib200_read_result", "lokib200_job_create", "lokib200_job_solve", "lokib200_job_results",
            "lokib200_job_process_outputs", "lokib200_job_time_series", "lokib200_job_histograms", "lokib200_job_periodic",
-           "lokib200_job_periodic_diffusion", "lokib200_job_conditions", "lokib200_job_last_error", "lokib200_job_destroy"]
+           "lokib200_job_periodic_diffusion", "lokib200_job_conditions", "lokib200_job_evdf_max_speed", "lokib200_job_last_error", "lokib200_job_destroy"]
 # every symbol include/lokib200_host.h declares
 HOST_SYMBOLS = ["lokib200_setup_load", "lokib200_setup_destroy", "lokib200_setup_last_error", "lokib200_setup_job_count", "lokib200_setup_job_value",
                 "lokib200_setup_variable_condition", "lokib200_setup_processes", "lokib200_setup_config", "lokib200_setup_controls",
                 "lokib200_setup_process_description", "lokib200_setup_process_is_elastic", "lokib200_setup_energy_max_elastic",
                 "lokib200_setup_value", "lokib200_setup_dump", "lokib200_setup_warning_count", "lokib200_setup_warning",
-                "lokib200_eval_expression", "lokib200_eval_vector_expression"]
+                "lokib200_eval_expression", "lokib200_eval_vector_expression", "lokib200_report_create", "lokib200_report_from_job",
+                "lokib200_report_destroy", "lokib200_report_last_error", "lokib200_report_swarm", "lokib200_report_power", "lokib200_report_energy_cells",
+                "lokib200_report_eedf", "lokib200_report_rate_count", "lokib200_report_rate", "lokib200_output_create", "lokib200_output_write",
+                "lokib200_output_folder", "lokib200_output_last_error", "lokib200_output_destroy", "lokib200_run_setup", "lokib200_run_last_error"]
 
 
 def lib():
@@ -175,12 +195,14 @@ def lib():
     L.lokib200_get_rel_densities.argtypes = [vp, c_dp]
     L.lokib200_job_create.argtypes = [C.POINTER(vp), C.c_int32, C.POINTER(SolveControls), C.POINTER(vp)]
     L.lokib200_job_solve.argtypes = [vp, C.POINTER(SolveResults)]
+    L.lokib200_job_results.argtypes = [vp, C.POINTER(SolveResults)]
     L.lokib200_job_process_outputs.argtypes = [vp, c_dp, c_dp, c_dp, c_dp]
     L.lokib200_job_time_series.argtypes = [vp, c_dp, c_dp, c_dp, c_dp, c_dp]; L.lokib200_job_time_series.restype = C.c_int64
     L.lokib200_job_histograms.argtypes = [vp, c_dp, c_dp, c_dp, c_dp]
     L.lokib200_job_periodic.argtypes = [vp, c_dp, c_dp, c_dp, c_dp]
     L.lokib200_job_periodic_diffusion.argtypes = [vp, c_dp, c_dp]
     L.lokib200_job_conditions.argtypes = [vp, C.POINTER(Config), c_ip]
+    L.lokib200_job_evdf_max_speed.argtypes = [vp]; L.lokib200_job_evdf_max_speed.restype = C.c_double
     L.lokib200_job_last_error.argtypes = [vp]; L.lokib200_job_last_error.restype = C.c_char_p
     L.lokib200_job_destroy.argtypes = [vp]; L.lokib200_job_destroy.restype = None
     _bind_host(L)
@@ -208,6 +230,23 @@ def _bind_host(L):
     L.lokib200_setup_warning.argtypes = [vp, C.c_int32]; L.lokib200_setup_warning.restype = C.c_char_p
     L.lokib200_eval_expression.argtypes = [C.c_char_p, c_ip]; L.lokib200_eval_expression.restype = C.c_double
     L.lokib200_eval_vector_expression.argtypes = [C.c_char_p, c_dp, C.c_int64, c_ip]; L.lokib200_eval_vector_expression.restype = C.c_int64
+    L.lokib200_report_create.argtypes = [vp, C.c_int32, C.POINTER(JobData), C.POINTER(vp)]
+    L.lokib200_report_from_job.argtypes = [vp, C.c_int32, vp, C.POINTER(vp)]
+    L.lokib200_report_destroy.argtypes = [vp]; L.lokib200_report_destroy.restype = None
+    L.lokib200_report_last_error.argtypes = [vp]; L.lokib200_report_last_error.restype = C.c_char_p
+    L.lokib200_report_swarm.argtypes = [vp, C.c_char_p, c_ip]; L.lokib200_report_swarm.restype = C.c_double
+    L.lokib200_report_power.argtypes = [vp, C.c_char_p, C.c_char_p, c_ip]; L.lokib200_report_power.restype = C.c_double
+    L.lokib200_report_energy_cells.argtypes = [vp]
+    L.lokib200_report_eedf.argtypes = [vp, c_dp, c_dp, c_dp, c_dp]
+    L.lokib200_report_rate_count.argtypes = [vp, C.c_int32]
+    L.lokib200_report_rate.argtypes = [vp, C.c_int32, C.c_int32, c_ip, c_dp, c_dp, c_dp, c_dp, C.POINTER(C.c_char_p)]
+    L.lokib200_output_create.argtypes = [vp, C.c_char_p, C.POINTER(vp)]
+    L.lokib200_output_write.argtypes = [vp, vp]
+    L.lokib200_output_folder.argtypes = [vp]; L.lokib200_output_folder.restype = C.c_char_p
+    L.lokib200_output_last_error.argtypes = [vp]; L.lokib200_output_last_error.restype = C.c_char_p
+    L.lokib200_output_destroy.argtypes = [vp]; L.lokib200_output_destroy.restype = None
+    L.lokib200_run_setup.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_int32, C.c_int32, C.c_int32, C.POINTER(RunSummary)]
+    L.lokib200_run_last_error.argtypes = []; L.lokib200_run_last_error.restype = C.c_char_p
 
 
 def _dp(a):
@@ -520,3 +559,103 @@ def eval_vector_expression(expr):
     out = np.zeros(max(int(n), 1))
     L.lokib200_eval_vector_expression(expr.encode(), _dp(out), n, C.byref(ok))
     return out[:n]
+
+
+class Report:
+    """Post-processing of one finished job (include/lokib200_host.h lokib200_report_*): distributions, power balance, rate
+    coefficients and swarm parameters.  Build it from a solved Job, or from raw arrays (`data`: dict with the JobData fields)."""
+
+    def __init__(self, setup, job_index, job=None, data=None):
+        L = lib()
+        self.L = L
+        self.setup = setup
+        h = C.c_void_p()
+        if job is not None:
+            rc = L.lokib200_report_from_job(setup.h, int(job_index), job.h, C.byref(h))
+        else:
+            jd = JobData()
+            self._keep = []
+            for name, ctype in JobData._fields_:
+                v = data.get(name)
+                if name == "results":
+                    self._keep.append(v); jd.results = C.pointer(v)
+                elif ctype is c_dp:
+                    if v is not None:
+                        a = np.ascontiguousarray(v, dtype=np.float64); self._keep.append(a); setattr(jd, name, _dp(a))
+                else:
+                    setattr(jd, name, v)
+            rc = L.lokib200_report_create(setup.h, int(job_index), C.byref(jd), C.byref(h))
+        if rc != 0:
+            raise LokiB200Error(L.lokib200_report_last_error(None).decode())
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.lokib200_report_destroy(self.h); self.h = None
+
+    __del__ = close
+
+    def swarm(self, name):
+        ok = C.c_int32(0)
+        v = self.L.lokib200_report_swarm(self.h, name.encode(), C.byref(ok))
+        if not ok.value:
+            raise KeyError(name)
+        return float(v)
+
+    def power(self, name, gas=None):
+        ok = C.c_int32(0)
+        v = self.L.lokib200_report_power(self.h, name.encode(), gas.encode() if gas else None, C.byref(ok))
+        if not ok.value:
+            raise KeyError(name)
+        return float(v)
+
+    def eedf(self):
+        n = self.L.lokib200_report_energy_cells(self.h)
+        a = [np.zeros(n) for _ in range(4)]
+        self.L.lokib200_report_eedf(self.h, *[_dp(x) for x in a])
+        return dict(energy=a[0], eedf=a[1], first_anisotropy=a[2], second_anisotropy=a[3])
+
+    def rates(self, extra=False):
+        out = []
+        for i in range(self.L.lokib200_report_rate_count(self.h, int(extra))):
+            cid = C.c_int32(); v = [C.c_double() for _ in range(4)]; d = C.c_char_p()
+            self.L.lokib200_report_rate(self.h, int(extra), i, C.byref(cid), *[C.byref(x) for x in v], C.byref(d))
+            out.append(dict(id=cid.value, ine=v[0].value, sup=v[1].value, ine_mc=v[2].value, sup_mc=v[3].value, description=(d.value or b"").decode()))
+        return out
+
+
+class Output:
+    """The reference's output folder (Headers/Output.h): setup.txt at creation, the selected data files per written job."""
+
+    def __init__(self, setup, output_root):
+        L = lib()
+        self.L = L
+        h = C.c_void_p()
+        if L.lokib200_output_create(setup.h, os.fsencode(output_root), C.byref(h)) != 0:
+            raise LokiB200Error(L.lokib200_output_last_error(None).decode())
+        self.h = h
+
+    @property
+    def folder(self):
+        return self.L.lokib200_output_folder(self.h).decode()
+
+    def write(self, report):
+        if self.L.lokib200_output_write(self.h, report.h) != 0:
+            raise LokiB200Error(self.L.lokib200_output_last_error(self.h).decode())
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.lokib200_output_destroy(self.h); self.h = None
+
+    __del__ = close
+
+
+def run_setup(input_dir, setup_file, output_root, n_devices=1, first_device=0, verbose=True):
+    """The reference executable's main loop on the GPU engine (include/lokib200_host.h lokib200_run_setup)."""
+    L = lib()
+    summary = RunSummary()
+    rc = L.lokib200_run_setup(os.fsencode(input_dir), os.fsencode(setup_file), os.fsencode(output_root), int(n_devices), int(first_device), int(bool(verbose)),
+                              C.byref(summary))
+    if rc != 0:
+        raise LokiB200Error(L.lokib200_run_last_error().decode())
+    return summary

@@ -84,6 +84,8 @@ struct lokib200_job {
   std::vector<Mat9> fluxDiffusionCoeffs_periodic, bulkDiffusionCoeffs_periodic;
   // histogram carry of earlier energy grids (BMC.C:1497-1548) and final sums
   bool histGridSet = false;
+  double evdfMaxSpeed = 0;
+  bool solved = false;
   std::vector<double> carryEeh, carryEah, carryEehPeriodic;
   double elapsed = 0;
   std::vector<double> res, tmp;
@@ -269,6 +271,7 @@ struct lokib200_job {
       maxEedfEnergy = 1.2 * maxElecEnergy;                                              // :1862
       for (auto* e : engines) { int rc = lokib200_set_histogram_grid(e, maxEedfEnergy); if (rc) return engineFail(e, rc); }
       histGridSet = true;
+      evdfMaxSpeed = std::sqrt(2.0 * maxEedfEnergy * 1.6021766208e-19 / 9.10938356e-31);   // :1877, fixed from here on
       return getTimeDependDistributions();                                              // :1891
     }
     return 0;
@@ -431,10 +434,8 @@ int lokib200_job_create(lokib200_engine* const* engines, int32_t n_engines, cons
   return 0;
 }
 
-int lokib200_job_solve(lokib200_job* j, lokib200_solve_results* r) {
-  if (!j) return LOKIB200_ERR_INVALID;
-  const int rc = j->evaluateEEDF();
-  if (r) {
+static void fillResults(const lokib200_job* j, lokib200_solve_results* r) {
+  {
     std::memset(r, 0, sizeof(*r));
     r->averaged_mean_energy = j->averagedMeanEnergy; r->averaged_mean_energy_error = j->averagedMeanEnergyError;
     for (int a = 0; a < 3; ++a) {
@@ -454,6 +455,13 @@ int lokib200_job_solve(lokib200_job* j, lokib200_solve_results* r) {
     r->n_table_rebuilds = j->nTableRebuilds;
     r->good_statistical_errors = j->goodStatisticalErrors; r->stopped_by_max_collisions = j->stoppedByMaxCollisions;
   }
+}
+
+int lokib200_job_solve(lokib200_job* j, lokib200_solve_results* r) {
+  if (!j) return LOKIB200_ERR_INVALID;
+  const int rc = j->evaluateEEDF();
+  j->solved = (rc == 0);
+  if (r) fillResults(j, r);
   return rc;
 }
 
@@ -503,6 +511,14 @@ int lokib200_job_periodic_diffusion(const lokib200_job* j, double* fd, double* b
   }
   return 0;
 }
+
+int lokib200_job_results(const lokib200_job* j, lokib200_solve_results* r) {
+  if (!j || !r || !j->solved) return LOKIB200_ERR_INVALID;
+  fillResults(j, r);
+  return 0;
+}
+
+double lokib200_job_evdf_max_speed(const lokib200_job* j) { return j ? j->evdfMaxSpeed : 0.0; }
 
 int lokib200_job_conditions(const lokib200_job* j, lokib200_config* cfg, int32_t* n_processes) {
   if (!j) return LOKIB200_ERR_INVALID;

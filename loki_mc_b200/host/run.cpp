@@ -1,0 +1,112 @@
+// run.cpp -- lokib200_run_setup: the reference's main loop (Sources/lokimc.C:14-42 LoKISimulation, Headers/Setup.h:92-227 initializeSimulation /
+// nextJob, :948-957 finishSimulation) over this library: parse the setup, and for every job build the engines, solve, post-process, write.
+#include <chrono>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "../../include/lokib200_host.h"
+#include "report.h"
+#include "setup_input.h"
+
+namespace {
+
+thread_local std::string g_run_error;
+
+struct Engines {
+  std::vector<lokib200_engine*> e;
+  ~Engines() { for (auto* p : e) lokib200_destroy(p); }
+};
+struct JobHandle {
+  lokib200_job* j = nullptr;
+  ~JobHandle() { if (j) lokib200_job_destroy(j); }
+};
+
+}  // namespace
+
+extern "C" {
+
+const char* lokib200_run_last_error(void) { return g_run_error.c_str(); }
+
+int lokib200_run_setup(const char* input_dir, const char* setup_file, const char* output_root, int32_t n_devices, int32_t first_device, int32_t verbose,
+                       lokib200_run_summary* summary) {
+  const auto start = std::chrono::high_resolution_clock::now();
+  if (!input_dir || !setup_file || !output_root || n_devices < 1) { g_run_error = "lokib200_run_setup: invalid argument"; return LOKIB200_ERR_INVALID; }
+  if (summary) *summary = lokib200_run_summary{};
+  try {
+    lokihost::SetupInput in(input_dir, setup_file);
+    for (const auto& w : in.mixture->warnings) std::printf("\033[1;33mPay attention to the following warning:\n%s\n\033[0m", w.c_str());
+    if (verbose) {
+      const std::string on = in.tree->value("gui.isOn");
+      bool show = false;
+      if (on == "true" || on == "True" || on == "1") for (const auto& o : in.tree->childNames("gui.terminalDisp")) show = show || o == "setup";
+      if (show) std::printf("%s", in.tree->dump().c_str());   // FieldInfo::printSetupInfo
+      std::printf("Starting simulation...\n");
+    }
+    lokihost::OutputWriter out(in, output_root);
+    const lokib200_process_soa soa = in.processes.soa();
+    for (int job = 0; job < in.nJobs(); ++job) {
+      lokib200_config cfg = in.config(job);
+      const int64_t total = cfg.n_electrons, per = total / n_devices;
+      if (per < 1) throw lokihost::SetupError("numericsMC.nElectrons is smaller than the number of devices");
+      Engines eng;
+      uint64_t first = 0;
+      for (int g = 0; g < n_devices; ++g) {
+        lokib200_config c = cfg;
+        c.device = first_device + g;
+        c.n_electrons = per + (g == 0 ? total - per * n_devices : 0);   // shards by global electron id; the remainder goes to the first
+        c.first_electron_id = first;
+        first += static_cast<uint64_t>(c.n_electrons);
+        lokib200_engine* h = nullptr;
+        if (lokib200_create(&c, &h)) throw lokihost::SetupError(std::string("engine: ") + lokib200_last_error(nullptr));
+        eng.e.push_back(h);
+        if (lokib200_set_processes(h, &soa)) throw lokihost::SetupError(std::string("engine: ") + lokib200_last_error(h));
+      }
+      const lokib200_solve_controls ctl = in.controls();
+      JobHandle jh;
+      if (lokib200_job_create(eng.e.data(), n_devices, &ctl, &jh.j)) throw lokihost::SetupError("could not create the job");
+      lokib200_solve_results res;
+      if (lokib200_job_solve(jh.j, &res)) throw lokihost::SetupError(lokib200_job_last_error(jh.j));
+      if (res.stopped_by_max_collisions)   // BMC.C:398-415
+        std::printf("\033[1;33mPay attention to the following warning:\nMonte Carlo simulation ended after reaching ''maxCollisionsAfterSteadyState'' indicated in the setup file. "
+                    "[%s = %g]\n\033[0m", in.wc.variableCondition.c_str(), in.jobValue(job));
+      int32_t P = 0;
+      lokib200_config jc;
+      lokib200_job_conditions(jh.j, &jc, &P);
+      const size_t nE = jc.n_energy_cells, nC = jc.n_cos_cells, nR = jc.n_radial_cells, nA = jc.n_axial_cells, nPh = jc.excitation_omega != 0 ? jc.n_phases : 0;
+      lokihost::JobData d;
+      d.res = res; d.nElectrons = static_cast<double>(jc.n_electrons); d.evdfMaxSpeed = lokib200_job_evdf_max_speed(jh.j);
+      d.rateCoeffsMC.resize(P); d.powerGain.resize(P); d.powerLoss.resize(P); d.counts.resize(P);
+      lokib200_job_process_outputs(jh.j, d.rateCoeffsMC.data(), d.powerGain.data(), d.powerLoss.data(), d.counts.data());
+      d.eehSum.resize(nE); d.eahSum.resize(nE * nC); d.evhSum.resize(nR * nA); d.eehSumPeriodic.resize(nPh * nE);
+      if (lokib200_job_histograms(jh.j, d.eehSum.data(), d.eahSum.data(), d.evhSum.data(), nPh ? d.eehSumPeriodic.data() : nullptr))
+        throw lokihost::SetupError(std::string("histograms: ") + lokib200_job_last_error(jh.j));
+      if (!jc.is_cylindrically_symmetric) { d.eahSum.clear(); d.evhSum.clear(); }
+      const int64_t n = lokib200_job_time_series(jh.j, nullptr, nullptr, nullptr, nullptr, nullptr);
+      d.samplingTimes.resize(n); d.meanEnergies.resize(n); d.meanPositions.resize(3 * n); d.meanVelocities.resize(3 * n); d.positionCovariances.resize(9 * n);
+      lokib200_job_time_series(jh.j, d.samplingTimes.data(), d.meanEnergies.data(), d.meanPositions.data(), d.meanVelocities.data(), d.positionCovariances.data());
+      if (nPh) {
+        d.pointsPerPhase.resize(nPh); d.meanEnergiesPeriodic.resize(nPh); d.fluxVelocitiesPeriodic.resize(3 * nPh); d.bulkVelocitiesPeriodic.resize(3 * nPh);
+        d.fluxDiffusionPeriodic.resize(9 * nPh); d.bulkDiffusionPeriodic.resize(9 * nPh);
+        lokib200_job_periodic(jh.j, d.pointsPerPhase.data(), d.meanEnergiesPeriodic.data(), d.fluxVelocitiesPeriodic.data(), d.bulkVelocitiesPeriodic.data());
+        lokib200_job_periodic_diffusion(jh.j, d.fluxDiffusionPeriodic.data(), d.bulkDiffusionPeriodic.data());
+      }
+      lokihost::Report rep(in, job, std::move(d));
+      out.write(rep);
+      if (verbose)
+        std::printf("job %d/%d  %s = %g : mean energy %.6e eV (rel. err %.2e), %lld integration points, %.3e collisions, power balance %.2e, %.2f s\n", job + 1, in.nJobs(),
+                    in.wc.variableCondition.c_str(), in.jobValue(job), res.averaged_mean_energy, res.averaged_mean_energy_error / res.averaged_mean_energy,
+                    static_cast<long long>(res.n_integration_points), res.total_collisions, res.power_balance_rel_error, res.elapsed_seconds);
+      if (summary) {
+        summary->n_jobs = job + 1; summary->last_mean_energy = res.averaged_mean_energy; summary->total_collisions += res.total_collisions + res.null_collisions;
+        summary->device_seconds += res.elapsed_seconds;
+      }
+    }
+    const double elapsed = std::chrono::duration<double>(std::chrono::high_resolution_clock::now() - start).count();
+    if (summary) summary->elapsed_seconds = elapsed;
+    if (verbose) std::printf("Finished!\nElapsed time is %g seconds.\n", elapsed);   // Setup.h:948-957
+    return LOKIB200_OK;
+  } catch (const std::exception& e) { g_run_error = e.what(); return LOKIB200_ERR_INVALID; }
+}
+
+}  // extern "C"

@@ -503,7 +503,7 @@ double linInterp(const std::vector<double>& x, const std::vector<double>& y, dou
 }
 
 // Collision::interpolatedCrossSection (Collision.C:232-289) at the points `en`
-std::vector<double> interpolated(const Collision& c, bool momTransf, const std::vector<double>& en) {
+std::vector<double> interpolatedImpl(const Collision& c, bool momTransf, const std::vector<double>& en) {
   std::vector<double> out(en.size(), 0.0);
   int minIndex = -1;
   if (c.type == "Effective" || c.type == "Elastic") minIndex = 0;
@@ -515,7 +515,7 @@ std::vector<double> interpolated(const Collision& c, bool momTransf, const std::
 }
 
 // Collision::superElasticCrossSection (Collision.C:291-353), Klein-Rosseland
-std::vector<double> superElastic(const Collision& c, bool momTransf, const std::vector<double>& en) {
+std::vector<double> superElasticImpl(const Collision& c, bool momTransf, const std::vector<double>& en) {
   if (c.target->statisticalWeight == NON_DEF) throw SetupError("The statistical weight of the state '" + c.target->name + "' is not defined.\nThe super elastic cross section of the collision '" + c.description() + " cannot be evaluated.\n");
   if (c.products[0]->statisticalWeight == NON_DEF) throw SetupError("The statistical weight of the state '" + c.products[0]->name + "' is not defined.\nThe super elastic cross section of the collision '" + c.description() + " cannot be evaluated.\n");
   std::vector<double> out(en.size(), 0.0);
@@ -523,7 +523,7 @@ std::vector<double> superElastic(const Collision& c, bool momTransf, const std::
   if (en[0] == 0) { if (en.size() == 1) return out; minIndex = 1; }
   std::vector<double> shifted(en.size());
   for (size_t i = 0; i < en.size(); ++i) shifted[i] = en[i] + c.threshold;
-  auto interp = interpolated(c, momTransf, shifted);
+  auto interp = interpolatedImpl(c, momTransf, shifted);
   const double ratio = c.target->statisticalWeight / c.products[0]->statisticalWeight;
   for (auto& v : interp) v = v * ratio;
   for (size_t i = minIndex; i < en.size(); ++i) out[i] = (1.0 + c.threshold / en[i]) * interp[i];
@@ -563,6 +563,12 @@ int angularModelId(const std::string& t) {
 }
 
 }  // namespace
+
+std::vector<double> interpolatedCrossSection(const Collision& c, bool momTransf, const std::vector<double>& energies) { return interpolatedImpl(c, momTransf, energies); }
+std::vector<double> superElasticCrossSection(const Collision& c, bool momTransf, const std::vector<double>& energies) {
+  if (!c.isReverse) throw SetupError("Collision '" + c.description() + " is not defined as bidirectional.\n");
+  return superElasticImpl(c, momTransf, energies);
+}
 
 // ------------------------------------------------------------------ ontology ------------------------------------------------------------------
 std::string Collision::description() const {   // Collision.C:88-125
@@ -902,10 +908,10 @@ CrossSection Mixture::elasticFromEffective(Gas* g) {   // EedfGas.C:171-301
   while (pop.size() < static_cast<size_t>(maxID) + 1) pop.push_back(0.0);
   for (Collision* c : g->collisions) {
     if (c->type == "Effective" || c->type == "Elastic") continue;
-    const auto xs = interpolated(*c, true, el.e);
+    const auto xs = interpolatedImpl(*c, true, el.e);
     for (size_t i = 0; i < el.e.size(); ++i) el.v[i] -= pop[c->target->id] * xs[i];
     if (c->isReverse) {
-      const auto sup = superElastic(*c, true, el.e);
+      const auto sup = superElasticImpl(*c, true, el.e);
       for (size_t i = 0; i < el.e.size(); ++i) el.v[i] -= pop[c->products[0]->id] * sup[i];
     }
   }
@@ -1061,9 +1067,106 @@ lokib200_process_soa ProcessSet::soa() const {
   return p;
 }
 
+// ------------------------------------------------------------------ setup self-diagnostic ------------------------------------------------------------------
+// Setup::selfDiagnostic (Setup.h:576-945), the checks that apply to a boltzmannMC setup; messages are the reference's.
+static void selfDiagnostic(const SetupTree& t) {
+  auto missing = [](const std::string& field, const std::string& section) {
+    return SetupError("Error found in the configuration of the setup file.\n''" + field + "'' field not found in the ''" + section +
+                      "'' section of the setup file.\nPlease, fix the problem and run the code again.");
+  };
+  auto wrong = [](const std::string& field, const std::string& should, bool quoted = true) {
+    const std::string q = quoted ? "''" : "";
+    return SetupError("Error found in the configuration of the setup file.\nWrong value for the field " + q + field + q + ".\nValue should " + should +
+                      ".\nPlease, fix the problem and run the code again.");
+  };
+  auto logical = [](const std::string& v) { return v == "true" || v == "True" || v == "1" || v == "0" || v == "false" || v == "False"; };
+  auto isTrue = [](const std::string& v) { return v == "true" || v == "True" || v == "1"; };
+  auto num = [&](const std::string& k) { return t.has(k) ? t.number(k) : 0.0; };
+  const std::string ek = "electronKinetics";
+  if (t.has(ek)) {
+    if (!t.has(ek + ".isOn")) throw missing("isOn", ek);
+    if (!logical(t.value(ek + ".isOn"))) throw wrong("electronKinetics>isOn", "be logical (''true'' or ''false'')", false);
+    if (isTrue(t.value(ek + ".isOn"))) {
+      if (!t.has(ek + ".eedfType")) throw missing("eedfType", ek);
+      const std::string type = t.value(ek + ".eedfType");
+      if (type != "boltzmannMC" && type != "prescribedEedf") throw wrong("electronKinetics>eedfType", "be: ''boltzmannMC'' or ''prescribedEedf''");
+      if (type == "boltzmannMC") {
+        if (!t.has(ek + ".ionizationOperatorType")) throw missing("ionizationOperatorType", ek);
+        const std::string ion = t.value(ek + ".ionizationOperatorType");
+        if (ion != "oneTakesAll" && ion != "equalSharing" && ion != "usingSDCS" && ion != "randomUniform")
+          throw wrong("electronKinetics>ionizationOperatorType", "be either: ''oneTakesAll'', ''equalSharing'', ''usingSDCS'' or ''randomUniform''");
+      }
+      if (!t.has(ek + ".LXCatFiles")) throw missing("LXCatFiles", ek);
+      if (!t.has(ek + ".gasProperties")) throw missing("gasProperties", ek);
+      if (!t.has(ek + ".gasProperties.mass")) throw missing("mass", "electronKinetics>gasProperties");
+      if (!t.has(ek + ".gasProperties.fraction")) throw missing("fraction", "electronKinetics>gasProperties");
+      if (!t.has(ek + ".stateProperties")) throw missing("stateProperties", ek);
+      if (!t.has(ek + ".stateProperties.population")) throw missing("population", "electronKinetics>stateProperties");
+      if (type.find("boltzmannMC") != std::string::npos) {
+        const std::string mc = ek + ".numericsMC";
+        if (!t.has(mc)) throw missing("numericsMC", ek);
+        if (!t.has(mc + ".nElectrons")) throw missing("nElectrons", "electronKinetics>numericsMC");
+        if (!t.has(mc + ".gasTemperatureEffect")) throw missing("gasTemperatureEffect", "electronKinetics>numericsMC");
+        const std::string gt = t.value(mc + ".gasTemperatureEffect");
+        if (gt != "false" && gt != "true" && gt != "smartActivation") throw wrong("electronKinetics>numericsMC", "be ''false'', ''true'' or ''smartActivation''", false);
+        for (const char* k : {"nEnergyCells", "nCosAngleCells", "nAxialVelocityCells", "nRadialVelocityCells", "nInterpPoints"})
+          if ((t.has(mc + "." + k) && num(mc + "." + k) <= 0) || std::fmod(num(mc + "." + k), 1) != 0)
+            throw wrong(std::string("electronKinetics>numericsMC>") + k, "be a single positive integer");
+        if (t.has(mc + ".synchronizationTimeXMaxCollisionFrequency") && num(mc + ".synchronizationTimeXMaxCollisionFrequency") <= 0)
+          throw wrong("electronKinetics>numericsMC>synchronizationTimeXMaxCollisionFrequency", "be a single positive number");
+        if ((t.has(mc + ".synchronizationOverSampling") && num(mc + ".synchronizationOverSampling") < 1) || std::fmod(num(mc + ".synchronizationOverSampling"), 1) != 0)
+          throw wrong("electronKinetics>numericsMC>synchronizationOverSampling", "be a single integer >= 1");
+        if (t.has(mc + ".initialElecTempOverGasTemp") && num(mc + ".initialElecTempOverGasTemp") <= 0)
+          throw wrong("electronKinetics>numericsMC>initialElecTempOverGasTemp", "be a single positive number");
+        if (t.has(mc + ".minCollisionsBeforeSteadyState") && num(mc + ".minCollisionsBeforeSteadyState") < 0)
+          throw wrong("electronKinetics>numericsMC>minCollisionsBeforeSteadyState", "be a single non-negative number");
+        for (const char* k : {"maxCollisionsBeforeSteadyState", "maxCollisionsAfterSteadyState"})
+          if (t.has(mc + "." + k) && num(mc + "." + k) <= 0) throw wrong(std::string("electronKinetics>numericsMC>") + k, "be a single positive number");
+        if ((t.has(mc + ".nIntegrationPoints") && num(mc + ".nIntegrationPoints") < 500) || std::fmod(num(mc + ".nIntegrationPoints"), 1) != 0)
+          throw wrong("electronKinetics>numericsMC>nIntegrationPoints", "be a single integer >= 500");
+        if ((t.has(mc + ".nIntegrationPhases") && num(mc + ".nIntegrationPhases") < 1) || std::fmod(num(mc + ".nIntegrationPhases"), 1) != 0)
+          throw wrong("electronKinetics>numericsMC>nIntegrationPhases", "be a single integer > 1");
+        for (const char* k : {"nIntegratedSSTimes", "integratedAbsoluteTime"})
+          if (t.has(mc + "." + k) && num(mc + "." + k) <= 0) throw wrong(std::string("electronKinetics>numericsMC>") + k, "be a single positive number");
+        for (const char* k : {"meanEnergy", "fluxDriftVelocity", "fluxDiffusionCoeffs", "bulkDriftVelocity", "bulkDiffusionCoeffs", "powerBalance"})
+          if (t.has(mc + ".relError." + k) && num(mc + ".relError." + k) <= 0) throw wrong(std::string("electronKinetics>numericsMC>relError>") + k, "be a single positive number");
+      }
+      const std::string an = ek + ".anisotropicScattering";
+      if (t.has(an)) {
+        if (!t.has(an + ".isOn")) throw missing("isOn", "electronKinetics>anisotropicScattering");
+        if (!logical(t.value(an + ".isOn"))) throw wrong("electronKinetics>anisotropicScattering>isOn", "be logical (''true'' or ''false'')", false);
+        if (isTrue(t.value(an + ".isOn"))) {
+          if (!t.has(an + ".collisions")) throw missing("collisions", "electronKinetics>anisotropicScattering");
+          if (!t.has(an + ".angleNumber")) throw missing("angleNumber", "electronKinetics>anisotropicScattering");
+          if (num(an + ".angleNumber") <= 0 || std::fmod(num(an + ".angleNumber"), 1) != 0) throw wrong("electronKinetics>anisotropicScattering>angleNumber", "be a single positive integer");
+        }
+      }
+    }
+  }
+  if (!isTrue(t.value(ek + ".isOn")))
+    throw SetupError("Error found in the configuration of the setup file.\n''electronKinetics'' module is not activated.\nPlease, fix the problem and run the code again.");
+  for (const char* sec : {"gui", "output"}) {
+    const std::string s2 = sec;
+    if (!t.has(s2)) continue;
+    if (!t.has(s2 + ".isOn")) throw missing("isOn", s2);
+    if (!logical(t.value(s2 + ".isOn"))) throw wrong(s2 + ">isOn", "be logical (''true'' or ''false'')", false);
+  }
+  if (t.has("output") && isTrue(t.value("output.isOn"))) {
+    if (!t.has("output.dataFiles")) throw missing("dataFiles", "output");
+    static const char* files[] = {"eedf", "evdf", "swarmParameters", "rateCoefficients", "powerBalance", "lookUpTable", "MCTemporalInfo", "MCTemporalInfo_periodic", "MCSimDetails"};
+    for (const auto& f : t.childNames("output.dataFiles")) {
+      bool ok = false;
+      for (const char* k : files) ok = ok || f == k;
+      if (!ok) throw SetupError("Error found in the configuration of the setup file.\nWrong value for the field ''gui>dataFiles''. Possible data files are: eedf, evdf, swarmParameters, "
+                                "rateCoefficients, powerBalance, lookUpTable, MCTemporalInfo, MCTemporalInfo_periodic, MCSimDetails.\nPlease, fix the problem and run the code again.");
+    }
+  }
+}
+
 // ------------------------------------------------------------------ one setup file ------------------------------------------------------------------
 SetupInput::SetupInput(const std::string& inputDir, const std::string& setupFile) {
   tree = std::make_unique<SetupTree>(inputDir, SetupTree::readFile(setupFile.rfind("/", 0) == 0 ? setupFile : inputDir + "/" + setupFile));   // an absolute path is taken as is
+  selfDiagnostic(*tree);
   const std::string eedfType = tree->value("electronKinetics.eedfType");
   if (eedfType != "boltzmannMC") throw SetupError("Please choose a valid 'electronKinetics->eedfType' in the setup file: this build implements 'boltzmannMC' (found '" + eedfType + "').");
   for (const char* key : {"electronKinetics.ionizationOperatorType", "electronKinetics.LXCatFiles", "electronKinetics.numericsMC.nElectrons", "electronKinetics.numericsMC.gasTemperatureEffect"})

@@ -100,6 +100,11 @@ struct Collision {
   std::string description() const;
 };
 
+// Collision::interpolatedCrossSection / superElasticCrossSection (Collision.C:232-353): linear interpolation of the raw curve, 0 outside;
+// Klein-Rosseland relation for the reverse direction
+std::vector<double> interpolatedCrossSection(const Collision& c, bool momTransf, const std::vector<double>& energies);
+std::vector<double> superElasticCrossSection(const Collision& c, bool momTransf, const std::vector<double>& energies);
+
 struct ProcessSet {   // what BoltzmannMC holds per process (BMC.h:86-118), ready for lokib200_set_processes
   std::vector<int32_t> type, isSuperelastic, isElastic, angularModel, gasFirst, gasLast;
   std::vector<double> ap0, ap1, swf, emin, emax, relDensity, targetMass, reducedMass, energyLoss, thermalStd, wParameter, gasFraction;

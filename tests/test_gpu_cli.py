@@ -1,0 +1,97 @@
+"""End to end on the GPU: setup file in, output folder out (lokib200_run_setup, the reference executable's main loop), compared with
+the folder the reference wrote for the same setup (tests/golden/output_*.tgz): same files, same layout, swarm results within the
+statistical errors the two runs report."""
+import os
+import re
+import subprocess
+import sys
+import tarfile
+import tempfile
+
+import pytest
+
+import loki_mc_b200 as lk
+from test_host_output import NUM
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+FIX_INPUT = os.path.join(HERE, "fixtures", "Input")
+GOLD = os.path.join(HERE, "golden")
+
+
+def _value(path, label):
+    """value and relative std (%) of a '<label> = x (unit) ; Rel. std: y%' line of swarmParameters.txt (first occurrence)"""
+    for line in open(path):
+        if line.strip().startswith(label):
+            nums = NUM.findall(line)
+            return float(nums[0]), (float(nums[1]) if len(nums) > 1 else 0.0)
+    raise AssertionError("no line %r in %s" % (label, path))
+
+
+@pytest.mark.parametrize("setup,folder,n_electrons", [("setup_out_dc", "fx_dc", 20000), ("setup_out_ac", "fx_ac", 20000)])
+def test_run_setup_writes_the_reference_folder(setup, folder, n_electrons):
+    with tempfile.TemporaryDirectory() as tmp:
+        with tarfile.open(os.path.join(GOLD, "output_%s.tgz" % folder)) as t:
+            t.extractall(os.path.join(tmp, "ref"), filter="data")
+        ref = os.path.join(tmp, "ref", folder)
+        text = open(os.path.join(FIX_INPUT, "fx", setup + ".in")).read().replace("nElectrons: 400", "nElectrons: %d" % n_electrons)
+        path = os.path.join(tmp, "job.in")
+        with open(path, "w") as f:
+            f.write(text)
+        summary = lk.run_setup(FIX_INPUT, path, os.path.join(tmp, "out"), verbose=False)
+        out = os.path.join(tmp, "out", folder)
+        n_files = 0
+        for dirpath, _, names in os.walk(ref):
+            for name in names:
+                if name.endswith(".raw.bin"):
+                    continue
+                mine = os.path.join(out, os.path.relpath(os.path.join(dirpath, name), ref))
+                assert os.path.exists(mine), "missing " + mine
+                n_files += 1
+                if name in ("MCTemporalInfo.txt", "setup.txt"):          # row count depends on the run; setup.txt differs in nElectrons
+                    assert open(mine).readline() == open(os.path.join(dirpath, name)).readline()
+                    continue
+                a = [NUM.sub("#", x) for x in open(mine).read().split("\n")]
+                b = [NUM.sub("#", x) for x in open(os.path.join(dirpath, name)).read().split("\n")]
+                assert len(a) == len(b), name
+                for x, y in zip(a, b):
+                    if "Elapsed" in y or "number of integration points" in y:
+                        continue
+                    assert re.sub(r"[-+]?(nan|inf)", "#", x) == re.sub(r"[-+]?(nan|inf)", "#", y), "%s:\n%r\n%r" % (name, x, y)
+        assert n_files >= 10 and summary.n_jobs == (2 if folder == "fx_dc" else 1)
+        subs = [d for d in sorted(os.listdir(ref)) if os.path.isdir(os.path.join(ref, d))] or [""]
+        for sub in subs:
+            mine, theirs = os.path.join(out, sub, "swarmParameters.txt"), os.path.join(ref, sub, "swarmParameters.txt")
+            for label, floor in (("Mean energy", 0.01), ("Reduced transverse diffusion coefficient", 0.05), ("Reduced longitudinal diffusion coefficient", 0.08)):
+                v, e = _value(mine, label); w, g = _value(theirs, label)
+                sigma = max(floor, 3e-2 * (e ** 2 + g ** 2) ** 0.5)          # 3 sigma of the two reported relative errors (given in %)
+                assert abs(v - w) <= sigma * abs(w), "%s %s: %g vs reference %g (allowed %.1f%%)" % (sub, label, v, w, 100 * sigma)
+            # internal consistency of our own files
+            pb = [l for l in open(os.path.join(out, sub, "powerBalance.txt")) if "Relative Power Balance" in l][0]
+            assert float(NUM.findall(pb)[0]) < 2.0, pb
+
+
+def test_command_line_front_end():
+    exe = os.path.join(os.path.dirname(lk.lib_path()), "lokimc_b200")
+    if not os.path.exists(exe):
+        lk.build()
+    with tempfile.TemporaryDirectory() as tmp:
+        os.symlink(FIX_INPUT, os.path.join(tmp, "Input"))
+        text = open(os.path.join(FIX_INPUT, "fx", "setup_out_dc.in")).read().replace("[20,80]", "40").replace("nElectrons: 400", "nElectrons: 5000")
+        with open(os.path.join(tmp, "cli.in"), "w") as f:
+            f.write(text)
+        r = subprocess.run([exe, os.path.join(tmp, "cli.in"), "1"], cwd=tmp, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+        assert r.returncode == 0, r.stdout
+        assert "Finished!" in r.stdout and "Elapsed time is" in r.stdout
+        assert sorted(os.listdir(os.path.join(tmp, "Output", "fx_dc"))) == sorted(
+            ["MCSimDetails.txt", "MCTemporalInfo.txt", "eedf.txt", "evdf.txt", "powerBalance.txt", "rateCoefficients.txt", "rateCoefficientsMC.txt", "setup.txt",
+             "swarmParameters.txt"])
+        # an invalid setup ends with the reference's message, a non-zero status and errorLog.txt
+        with open(os.path.join(tmp, "bad.in"), "w") as f:
+            f.write(text.replace("nIntegrationPoints: 500", "nIntegrationPoints: 10"))
+        r = subprocess.run([exe, os.path.join(tmp, "bad.in")], cwd=tmp, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=120)
+        assert r.returncode != 0 and "Program stopped due to the following error" in r.stdout
+        assert "Value should be a single integer >= 500" in open(os.path.join(tmp, "errorLog.txt")).read()
+        r = subprocess.run([sys.executable, "-m", "loki_mc_b200", os.path.join(tmp, "bad.in")], cwd=tmp, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True,
+                           timeout=300, env=dict(os.environ, PYTHONPATH=os.path.dirname(HERE)))
+        assert r.returncode == 1 and "single integer >= 500" in r.stdout

@@ -145,6 +145,12 @@ def test_setup_errors_are_reported_not_fatal():
             lk.Setup(FIX_INPUT, _write(tmp, "d.in", base.replace("eedfType: boltzmannMC", "eedfType: boltzmann")))
         with pytest.raises(lk.LokiB200Error, match="Could not parse line"):
             lk.Setup(FIX_INPUT, _write(tmp, "e.in", base.replace("  gasTemperature: 350", "  gasTemperature 350 K now")))
+        with pytest.raises(lk.LokiB200Error, match="nIntegrationPoints''.\nValue should be a single integer >= 500"):
+            lk.Setup(FIX_INPUT, _write(tmp, "g.in", base.replace("nIntegrationPoints: 1E3", "nIntegrationPoints: 100")))
+        with pytest.raises(lk.LokiB200Error, match="''gasTemperatureEffect'' field not found in the ''electronKinetics>numericsMC'' section"):
+            lk.Setup(FIX_INPUT, _write(tmp, "h.in", base.replace("    gasTemperatureEffect: smartActivation\n", "")))
+        with pytest.raises(lk.LokiB200Error, match="ionizationOperatorType''.\nValue should be either"):
+            lk.Setup(FIX_INPUT, _write(tmp, "i.in", base.replace("ionizationOperatorType: usingSDCS", "ionizationOperatorType: sharing")))
         # a state that becomes a target through a '<->' collision needs its own Elastic: gas Z has no Effective to derive it from
         zfile = open(os.path.join(FIX_INPUT, "fx", "Z_LXCat.txt")).read().replace("e + Z(1S0) -> e + Z(3P2)", "e + Z(1S0) <-> e + Z(3P2)")
         os.makedirs(os.path.join(tmp, "fx2"))
