@@ -243,15 +243,15 @@ OUTPUT_ALL = """output:
 """
 # small jobs whose files are compared with the reference's Output byte layout (oracle/gen_output_golden.py)
 SETUP_OUT_DC = SETUP_A.replace("logspace(0,2,5)", "[20,80]").replace("nElectrons: 1000", "nElectrons: 400") \
-    .replace("    nIntegrationPoints: 1E3\n", "    nIntegrationPoints: 500\n    nEnergyCells: 40\n    nCosAngleCells: 10\n    nRadialVelocityCells: 12\n    nAxialVelocityCells: 12\n") \
+    .replace("    nIntegrationPoints: 1E3\n", "    nIntegrationPoints: 500\n    maxCollisionsBeforeSteadyState: 600\n    nEnergyCells: 40\n    nCosAngleCells: 10\n    nRadialVelocityCells: 12\n    nAxialVelocityCells: 12\n") \
     .replace("  LXCatFiles:\n", "  LXCatFilesExtra:\n    - fx/XY_extra_LXCat.txt\n  LXCatFiles:\n") \
     .replace("      - XY(A3) = 3\n", "      - XY(A3) = 3\n      - XY(D1) = 1\n") \
     .replace("output:\n  isOn: false\n", OUTPUT_ALL % "fx_dc").replace("% setup A:", "% output test (DC, two jobs), from setup A:")
-SETUP_OUT_AC = SETUP_B.replace("[100,200,400]", "150").replace("nElectrons: 2E3", "nElectrons: 400") \
+SETUP_OUT_AC = SETUP_B.replace("[100,200,400]", "0").replace("nElectrons: 2E3", "nElectrons: 400") \
     .replace("    nEnergyCells: 500\n    nCosAngleCells: 40\n    nRadialVelocityCells: 60\n    nAxialVelocityCells: 80\n    nIntegrationPhases: 24\n",
              "    nEnergyCells: 30\n    nCosAngleCells: 8\n    nRadialVelocityCells: 10\n    nAxialVelocityCells: 10\n    nIntegrationPhases: 6\n") \
     .replace("    nIntegrationPoints: 1E3\n    nIntegratedSSTimes: 3\n    integratedAbsoluteTime: 1E-7\n", "    nIntegrationPoints: 500\n") \
-    .replace("    minCollisionsBeforeSteadyState: 10\n    maxCollisionsBeforeSteadyState: 2E3\n    maxCollisionsAfterSteadyState: 1E4\n", "") \
+    .replace("    minCollisionsBeforeSteadyState: 10\n    maxCollisionsBeforeSteadyState: 2E3\n    maxCollisionsAfterSteadyState: 1E4\n", "    maxCollisionsBeforeSteadyState: 1500\n") \
     .replace("    relError:\n      meanEnergy: 1E-2\n      fluxDriftVelocity: 2E-2\n      bulkDriftVelocity: 3E-2\n      fluxDiffusionCoeffs: 4E-2\n      bulkDiffusionCoeffs: 5E-2\n      powerBalance: 1E-3\n", "") \
     .replace("output:\n  isOn: false\n", OUTPUT_ALL % "fx_ac").replace("% setup B:", "% output test (AC + B, elecFieldAngle 30), from setup B:")
 
