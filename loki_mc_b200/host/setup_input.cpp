@@ -1189,7 +1189,8 @@ lokib200_config SetupInput::config(int job) const {   // BMC.h:262-289, BMC.C:43
   const double EN = pick(wc.reducedElecFieldArray, "reducedElecField"), BN = pick(wc.reducedMagFieldArray, "reducedMagField");
   const double angle = pick(wc.elecFieldAngleArray, "elecFieldAngle"), freq = pick(wc.excitationFrequencyArray, "excitationFrequency");
   c.n_electrons = static_cast<int64_t>(tree->number("electronKinetics.numericsMC.nElectrons"));
-  c.seed = 0x4C6F4B49ull + static_cast<uint64_t>(job);
+  c.seed = 0x4C6F4B49ull + static_cast<uint64_t>(job);   // reproducible by default; LOKIB200_SEED selects another realisation
+  if (const char* env = std::getenv("LOKIB200_SEED")) c.seed += 0x9E3779B97F4A7C15ull * std::strtoull(env, nullptr, 10);
   const std::string gt = tree->value("electronKinetics.numericsMC.gasTemperatureEffect");
   c.gas_temperature_effect = gt == "true" ? 1 : gt == "smartActivation" ? 2 : 0;
   const std::string ion = tree->value("electronKinetics.ionizationOperatorType");

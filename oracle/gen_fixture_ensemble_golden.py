@@ -22,7 +22,7 @@ from gen_ensemble_golden import KEYS  # noqa: E402
 FIX = os.path.join(HERE, "..", "tests", "fixtures", "Input", "fx")
 # (nElectrons, replicas wanted, attempts).  The reference aborts on an Eigen index assertion in a fraction of the AC runs (more often the
 # more electrons; it is built as its CMakeLists does, -O2 without NDEBUG), so the AC case uses fewer electrons and retries.
-PLAN = {"setup_out_dc": (20000, 4, 4), "setup_out_ac": (2000, 6, 30)}
+PLAN = {"setup_out_dc": (20000, 10, 10), "setup_out_ac": (2000, 8, 60)}
 EXTRA = ["Flux parameters/v_z'", "Bulk parameters/v_z'", "Parameters obtained from the EEDF/Momentum-transfer frequency",
          "Parameters obtained from the EEDF/Energy-relaxation frequency", "Energy parameters/Electron temperature"]
 

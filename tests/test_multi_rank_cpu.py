@@ -36,6 +36,7 @@ def _worker(rank, world, port, name, n, q):
     ens = lo.Ensemble(m, hi_i - lo_i, 77, lo_i); ens.set(s0[:, lo_i:hi_i])
     gathered = torch.zeros(world * L, dtype=torch.float64); out = torch.zeros(L, dtype=torch.float64)
     total = None
+    ring_rows, combined_rows = [], []
     for it in range(1, 4):
         r = ens.advance(nu, it / nu, it, population_control=0)
         st = ens.get(); mom_n = st.shape[1]
@@ -47,6 +48,11 @@ def _worker(rank, world, port, name, n, q):
         vec[HEADER:HEADER + P] = r["counts"]; vec[HEADER + P:HEADER + 2 * P] = r["gain"]; vec[HEADER + 2 * P:] = r["loss"]
         bench.combine_results(dist, world, torch.from_numpy(vec), gathered, out, SUM_COUNT, HEADER)
         total = out.clone() if total is None else total + out
+        ring_rows.append(torch.from_numpy(vec.copy())); combined_rows.append(out.clone())
+    # the batched form used by the device-resident loop: one all-gather for all three intervals gives the same vectors
+    ring = torch.stack(ring_rows)
+    comb = bench.combine_ring(dist, world, ring, torch.zeros(world * ring.numel(), dtype=torch.float64), SUM_COUNT, HEADER)
+    assert torch.equal(comb, torch.stack(combined_rows))
     if rank == 0:
         q.put((total.numpy(), out.numpy()))
     full = np.zeros((8, n))

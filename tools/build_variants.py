@@ -8,7 +8,7 @@ from concurrent.futures import ThreadPoolExecutor
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from loki_mc_b200._capi import NVCC_FLAGS  # noqa: E402
+from loki_mc_b200._capi import HOST_SOURCES, NVCC_FLAGS  # noqa: E402
 
 OUT = os.path.join(ROOT, "build", "variants")
 os.makedirs(OUT, exist_ok=True)
@@ -21,8 +21,8 @@ def build(spec):
     if "-fmad=true" in flags:
         base = [f for f in base if f != "-fmad=false"]
     cmd = ["/usr/local/cuda/bin/nvcc"] + base + ["-DLK_BENCH_ONLY"] + flags + ["-o", os.path.join(OUT, "lib_%s.so" % name),
-                                                                                os.path.join(ROOT, "loki_mc_b200", "csrc", "lokib200.cu"),
-                                                                                os.path.join(ROOT, "loki_mc_b200", "host", "boltzmann_mc.cpp")]
+                                                                                os.path.join(ROOT, "loki_mc_b200", "csrc", "lokib200.cu")] + \
+          [os.path.join(ROOT, "loki_mc_b200", "host", f) for f in HOST_SOURCES]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     return name, r.returncode, r.stdout[-400:]
 
