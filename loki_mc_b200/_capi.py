@@ -52,6 +52,9 @@ def build(force=False, verbose=False):
     cu_deps = [cu] + [os.path.join(SRC, f) for f in ("lk_stream.cuh", "lk_tile.cuh", "lk_kernels.cuh", "lk_physics.cuh")] + public
     host_deps = [os.path.join(PKG, "host", f) for f in HOST_HEADERS] + public
     compile_flags = [f for f in NVCC_FLAGS if f != "-shared"]
+    all_sources = cu_deps + host_deps + [os.path.join(PKG, "host", f) for f in HOST_SOURCES + ("lokimc_main.cpp",)]
+    if not force and not _stale(out, all_sources) and os.path.exists(os.path.join(PKG, "lokimc_b200")):
+        return out   # the object cache does not travel to the GPU box; a library newer than every source is up to date
     objs = []
     jobs = [(cu, os.path.join(objdir, "lokib200.o"), cu_deps)] + \
            [(os.path.join(PKG, "host", f), os.path.join(objdir, f[:-4] + ".o"), [os.path.join(PKG, "host", f)] + host_deps) for f in HOST_SOURCES]

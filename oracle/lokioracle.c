@@ -276,6 +276,7 @@ static double cos_chi(const lo_model* m, int k, double energy, double energy_aft
     case A_SURENDRA: return (2.0 + energy - 2.0 * pow(1.0 + energy, draw(d))) / energy;
     case A_COULOMB: {
       const double e = (m->ap0[k] == 0) ? energy : energy_after, s = m->ap1[k] / e, R = draw(d);
+      if (!(e > 0)) return 1.0 - 2.0 * R;   /* screening parameter -> inf (oneTakesAll ejects at eps = 0): the reference's expression is inf/inf = NaN there; its limit is isotropic */
       return (s + 1.0 - (2.0 * s + 1.0) * R) / (s + 1.0 - R);
     }
     default: return 1.0 - 2.0 * draw(d);                              /* isotropic */
