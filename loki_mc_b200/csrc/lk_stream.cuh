@@ -18,6 +18,7 @@
 // one-thread-per-electron kernel.  The schedule involves no atomics, hence it is deterministic.
 #pragma once
 #include "lk_tile.cuh"
+// (this file is the v10 form of the kernel: see the round structure below)
 
 namespace lk {
 
@@ -36,7 +37,9 @@ constexpr double TALLY_SCALE = 68719476736.0;
 
 __host__ __device__ inline size_t stream_smem_bytes(int P, int nEn_hist) {
   size_t b = static_cast<size_t>(SC_COLS) * POOL * 8;       // state columns (+ time, id)
-  b += static_cast<size_t>(STREAM_WARPS) * R_HEADER * 8;    // per-warp accumulators
+  b += static_cast<size_t>(R_HEADER) * 8;                   // result header of the CTA
+  b += static_cast<size_t>(STREAM_THREADS) * 8;             // per-thread field-gain sums
+  b += static_cast<size_t>(STREAM_WARPS) * 16;              // per-warp energy maxima (end of interval, any event)
   b += static_cast<size_t>(P) * 16;                         // gain, loss (fixed point)
   b += 16 * 8;                                              // scan scratch (64-bit warp totals)
   b += static_cast<size_t>(POOL) * 4;                       // draw counters
@@ -44,10 +47,21 @@ __host__ __device__ inline size_t stream_smem_bytes(int P, int nEn_hist) {
   b += static_cast<size_t>(nEn_hist) * 4;                   // energy histogram
   b += static_cast<size_t>(POOL) * 2 * 5;                   // five lists
   b += POOL;                                                // flags
+  b += 32;                                                  // rare-event counters
+  b += 64;                                                  // CTA-uniform round state (cursors, list lengths)
   return (b + 15) & ~static_cast<size_t>(15);
 }
+// rows of nu_tot staged in shared memory (all of them or none): the null test of every event reads two of them, and L1 is only what two
+// resident CTAs leave of the SM's 256 KB
+__host__ __device__ inline int stream_nu_rows(int P, int nE) {
+#ifdef LK_NO_NU_STAGE
+  return 0;
+#endif
+  const size_t base = stream_smem_bytes(P, 0), budget = (227u * 1024u) / 2u - 1024u;   // two CTAs per SM, 1 KB per CTA reserved by the driver
+  return (base + static_cast<size_t>(nE) * 8 <= budget) ? nE : 0;
+}
 
-struct StateId { State s; unsigned long long* id; };
+struct StateId { State s; unsigned long long* id; };   // the 8 columns of s are one allocation: column c starts at s.x + c * n
 
 // 8-byte asynchronous global -> shared copy (LDGSTS): the refill of a freed slot overlaps with the collision phase
 __device__ __forceinline__ void cp_async8(void* smem_dst, const void* gmem_src) {
@@ -80,13 +94,51 @@ __device__ __forceinline__ void tally_collisions_fx(int chosen, double dE, unsig
   }
 }
 
+// null test against a nu_tot table that may live in shared memory (generic loads); BMC.C:1035-1053 like cold_null_test
+__device__ __forceinline__ bool stream_null_test(const Model& m, const double* __restrict__ nu_tab, double eps, double nue, double u, double& Rnu, bool& clamped, bool& exceeded) {
+  Rnu = nue * u;
+  int i1, i2; double w1, w2;
+  cold_rows(m, eps, i1, i2, w1, w2);
+  clamped = (i1 == m.nE - 1);
+  const double nu_here = w1 * nu_tab[i1] + w2 * nu_tab[i2];
+  exceeded = nu_here > nue;
+  return !(Rnu > nu_here);                                         // BMC.C:1050
+}
+
+__device__ __forceinline__ int tid_now() { int t; asm volatile("mov.u32 %0, %%tid.x;" : "=r"(t)); return t; }   // re-read, never spilled
+
+// max of a non-negative double over the warp, folded into a shared slot by lane 0.  The bit pattern of a non-negative double orders like
+// an unsigned integer, so two REDUX (high word, then low word among the lanes that hold the high maximum) replace ten shuffles.
+__device__ __forceinline__ void warp_max_into(unsigned long long* slot, double v, int lane) {
+  const unsigned long long b = static_cast<unsigned long long>(__double_as_longlong(v));
+  const unsigned int hi = static_cast<unsigned int>(b >> 32), lo = static_cast<unsigned int>(b);
+  const unsigned int mh = __reduce_max_sync(FULL, hi);
+  const unsigned int ml = __reduce_max_sync(FULL, hi == mh ? lo : 0u);
+  if (lane == 0) { const unsigned long long mx = (static_cast<unsigned long long>(mh) << 32) | ml; if (mx > *slot) *slot = mx; }
+}
+
+enum : int { MC_BORN = 0, MC_ATT, MC_CLAMP, MC_NUEX, MC_COUNT };   // rare events: counted with shared atomics, not in registers
+// CTA-uniform state of a round lives in shared memory and is re-read where it is used: with 128 registers per thread every value that stays
+// live across the inlined collision code is a spill candidate, and local-memory spills miss the small L1 (profiles/r1_v10_*)
+enum : int { RS_IN = 0, RS_OUT, RS_LEN, RS_NFL, RS_NBC, RS_NBT, RS_NF, RS_COUNT };   // (the 64-bit ones, range start and flight count, sit in s_scan[8], s_scan[9])
+
+// Round structure (one CTA, 256 threads, POOL resident electrons):
+//   (1) block scan over the slot flags -> lists: F = [continuing | collided this round | refilled this round], R = [cold | thermal], O/K/I retire + refill
+//   (2) retire (dense stores) + refill (cp.async, lands during (3) and (4a))
+//   (3) collisions of list R                       -- no barrier after it: a warp that is done goes on with (4a)
+//   (4a) flights of the continuing electrons        -- touch neither the slots of (3) nor the refilled ones
+//        cp.async wait + barrier
+//   (4b) flights of the collided and refilled electrons; refilled electrons arrive with a free time, so their warps skip the draw's logarithm
+//   barrier
 template <int FIELD, int GT, bool SAMPLE>
 __global__ void __launch_bounds__(STREAM_THREADS, 2) k_advance_stream(const Model m, const StateId sid, const Lists L, const Pending pend, const AdvArgs a,
                                                                        const HistGrid h, double* __restrict__ partials) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* col = reinterpret_cast<double*>(smem_raw);                                        // [SC_COLS][POOL]
-  double (*s_acc)[R_HEADER] = reinterpret_cast<double (*)[R_HEADER]>(col + SC_COLS * POOL);
-  unsigned long long* s_gain = reinterpret_cast<unsigned long long*>(reinterpret_cast<double*>(s_acc) + STREAM_WARPS * R_HEADER);
+  double* s_hdr = col + SC_COLS * POOL;                                                     // [R_HEADER]
+  double* s_gf = s_hdr + R_HEADER;                                                          // [STREAM_THREADS] field gain, one slot per thread
+  unsigned long long* s_wmax = reinterpret_cast<unsigned long long*>(s_gf + STREAM_THREADS); // [STREAM_WARPS][2] bit patterns of non-negative doubles
+  unsigned long long* s_gain = s_wmax + 2 * STREAM_WARPS;
   unsigned long long* s_loss = s_gain + m.P;
   unsigned long long* s_scan = s_loss + m.P;                                                // [16]
   unsigned int* s_used = reinterpret_cast<unsigned int*>(s_scan + 16);                      // [POOL]
@@ -97,25 +149,36 @@ __global__ void __launch_bounds__(STREAM_THREADS, 2) k_advance_stream(const Mode
   unsigned short* listK = listO + POOL;                                                     // [POOL] input rank of a retiring slot refilled at once (0xFFFF: stays empty)
   unsigned short* listI = listK + POOL;                                                     // [POOL] refilled slots that were already empty (0xFFFF: see listK)
   unsigned char* flag = reinterpret_cast<unsigned char*>(listI + POOL);                     // [POOL]
+  unsigned int* s_misc = reinterpret_cast<unsigned int*>(flag + POOL);                      // [MC_COUNT]
+  volatile int* s_rs = reinterpret_cast<volatile int*>(s_misc + 8);                         // [RS_COUNT] round state
+  const size_t fixed_bytes = stream_smem_bytes(m.P, 0);
+  double* s_nu = reinterpret_cast<double*>(smem_raw + fixed_bytes);                         // [a.pad] nu_tot rows, when they fit (a.pad = 0 otherwise)
 
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  {
+  const int tid = tid_now();
   for (int k = tid; k < m.P; k += STREAM_THREADS) { s_gain[k] = 0; s_loss[k] = 0; s_cnt[k] = 0; }
-  for (int j = tid; j < STREAM_WARPS * R_HEADER; j += STREAM_THREADS) (&s_acc[0][0])[j] = 0;
+  if (tid < R_HEADER) s_hdr[tid] = 0;
+  s_gf[tid] = 0;
+  if (tid < 2 * STREAM_WARPS) s_wmax[tid] = 0ull;
+  if (tid < MC_COUNT) s_misc[tid] = 0;
+  for (int j = tid; j < static_cast<int>(a.pad); j += STREAM_THREADS) s_nu[j] = __ldg(&m.nu_tot[j]);
   reinterpret_cast<unsigned int*>(flag)[tid] = 0u;   // all slots FL_EMPTY
 
-  unsigned int n_null = 0, n_born = 0, n_att = 0, n_clamp = 0, n_nuex = 0;
-  double gain_field = 0, max_end = 0, max_seen = 0;
-  const uint32_t k0 = static_cast<uint32_t>(a.seed), k1 = static_cast<uint32_t>(a.seed >> 32);
-  double* const gcol[8] = {sid.s.x, sid.s.y, sid.s.z, sid.s.vx, sid.s.vy, sid.s.vz, sid.s.tcf, sid.s.nue};
-
-  // the CTA's range [lo, hi) of the ensemble; in/out cursors are CTA-uniform
-  const long long chunk = (((a.n + gridDim.x - 1) / gridDim.x) + 31) & ~31ll;
-  const long long lo = min(static_cast<long long>(blockIdx.x) * chunk, a.n), hi = min(lo + chunk, a.n);
-  long long in_ptr = lo, out_ptr = lo;
+  // the CTA's range [lo, lo + len) of the ensemble; cursors are CTA-uniform offsets into it.  Column c of the state is sid.s.x + lo + c * a.n.
+  if (tid == 0) {
+    const long long chunk = (((a.n + gridDim.x - 1) / gridDim.x) + 31) & ~31ll;
+    const long long lo = min(static_cast<long long>(blockIdx.x) * chunk, a.n);
+    s_rs[RS_IN] = 0; s_rs[RS_OUT] = 0; s_rs[RS_LEN] = static_cast<int>(min(lo + chunk, a.n) - lo);
+    *reinterpret_cast<volatile long long*>(&s_scan[8]) = lo;
+    *reinterpret_cast<volatile unsigned long long*>(&s_scan[9]) = 0ull;
+  }
+  }
   __syncthreads();
 
+#pragma unroll 1
   for (;;) {
     // ================= (1) block scan over the slot flags: build the lists of this round in slot order =================
+    const int tid = tid_now(), lane = tid & 31, warp = tid >> 5;
     const unsigned int f4 = reinterpret_cast<const unsigned int*>(flag)[tid];
     unsigned int cFl = 0, cRc = 0, cRt = 0, cRet = 0, cFree = 0;
 #pragma unroll
@@ -137,12 +200,14 @@ __global__ void __launch_bounds__(STREAM_THREADS, 2) k_advance_stream(const Mode
     const unsigned long long excl = before + incl - mine;
     const int nFl = static_cast<int>(total & 0xFFFu), nRc = static_cast<int>((total >> 12) & 0xFFFu), nRt = static_cast<int>((total >> 24) & 0xFFFu),
               nRet = static_cast<int>((total >> 36) & 0xFFFu), nFree = static_cast<int>((total >> 48) & 0xFFFu);
-    const int nRefill = static_cast<int>(min(static_cast<long long>(nFree), hi - in_ptr));
+    const int in_off = s_rs[RS_IN], out_off = s_rs[RS_OUT];
+    const int nRefill = min(nFree, s_rs[RS_LEN] - in_off);
     // collisions are run in whole CTA-iterations; everything parked is flushed when the flights alone cannot keep the CTA busy
     const bool flush = (nFl + nRefill < STREAM_THREADS);
     const int nBc = flush ? nRc : (nRc / STREAM_THREADS) * STREAM_THREADS, nBt = flush ? nRt : (nRt / STREAM_THREADS) * STREAM_THREADS;
     int eFl = static_cast<int>(excl & 0xFFFu), eRc = static_cast<int>((excl >> 12) & 0xFFFu), eRt = static_cast<int>((excl >> 24) & 0xFFFu),
         eRet = static_cast<int>((excl >> 36) & 0xFFFu), eFree = static_cast<int>((excl >> 48) & 0xFFFu);
+    const int baseC = nFl, baseT = nFl + nBc, baseI = nFl + nBc + nBt;   // F = [continuing | collided cold | collided thermal | refilled]
     unsigned int new_f4 = f4;
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
@@ -154,69 +219,84 @@ __global__ void __launch_bounds__(STREAM_THREADS, 2) k_advance_stream(const Mode
         listK[eRet] = (eFree < nRefill) ? static_cast<unsigned short>(eFree) : static_cast<unsigned short>(0xFFFF);
         ++eRet; f = FL_EMPTY;
       }
-      const int posF = eFl + min(eFree, nRefill) + min(eRc, nBc) + min(eRt, nBt);
       if (f == FL_EMPTY) {
-        if (eFree < nRefill) { listI[eFree] = retiring ? static_cast<unsigned short>(0xFFFF) : static_cast<unsigned short>(sl); listF[posF] = static_cast<unsigned short>(sl); f = FL_FLIGHT; }
+        if (eFree < nRefill) { listI[eFree] = retiring ? static_cast<unsigned short>(0xFFFF) : static_cast<unsigned short>(sl); listF[baseI + eFree] = static_cast<unsigned short>(sl); f = FL_FLIGHT; }
         ++eFree;
-      } else if (f == FL_FLIGHT) { listF[posF] = static_cast<unsigned short>(sl); ++eFl; }
-      else if (f == FL_REAL) { if (eRc < nBc) { listR[eRc] = static_cast<unsigned short>(sl); listF[posF] = static_cast<unsigned short>(sl); } ++eRc; }
-      else if (f == FL_REALT) { if (eRt < nBt) { listR[nBc + eRt] = static_cast<unsigned short>(sl); listF[posF] = static_cast<unsigned short>(sl); } ++eRt; }
+      } else if (f == FL_FLIGHT) { listF[eFl] = static_cast<unsigned short>(sl); ++eFl; }
+      else if (f == FL_REAL) { if (eRc < nBc) { listR[eRc] = static_cast<unsigned short>(sl); listF[baseC + eRc] = static_cast<unsigned short>(sl); } ++eRc; }
+      else if (f == FL_REALT) { if (eRt < nBt) { listR[nBc + eRt] = static_cast<unsigned short>(sl); listF[baseT + eRt] = static_cast<unsigned short>(sl); } ++eRt; }
       new_f4 = (new_f4 & ~(0xFFu << (8 * q))) | (f << (8 * q));
     }
     reinterpret_cast<unsigned int*>(flag)[tid] = new_f4;
     const int nF = nFl + nRefill + nBc + nBt;
+    if (tid == 0) {   // every electron in F flies once this round unless it attaches in (3): sum of nF - electrons = non-partial flights = real + null events
+      s_rs[RS_NFL] = nFl; s_rs[RS_NBC] = nBc; s_rs[RS_NBT] = nBt; s_rs[RS_NF] = nF;
+      *reinterpret_cast<volatile unsigned long long*>(&s_scan[9]) += static_cast<unsigned long long>(nF);
+    }
     __syncthreads();
     if (nF == 0 && nRet == 0) break;                               // nothing in flight, nothing parked, nothing to write back or load
+    const long long lo = *reinterpret_cast<volatile long long*>(&s_scan[8]);
+    double* const g0 = sid.s.x + lo;
+    unsigned long long* const gid = sid.id + lo;
 
     // ================= (2) retire + refill, dense: electron k of the list <-> global element cursor + k =================
-    for (int k = tid; k < nRet; k += STREAM_THREADS) {
+    for (int kb = warp * 32; kb < nRet; kb += STREAM_THREADS) {
+      const int k = kb + lane;
+      double eps_end = 0;
+      if (k < nRet) {
       const unsigned int e = listO[k];
       const int sl = static_cast<int>(e & 0x7FFFu);
-      const long long pos = out_ptr + k;
+      double* const gp = g0 + (out_off + k);
+      const double vx = col[SC_VX * POOL + sl], vy = col[SC_VY * POOL + sl], vz = col[SC_VZ * POOL + sl];
 #pragma unroll
-      for (int c = 0; c < 8; ++c) __stcs(&gcol[c][pos], col[c * POOL + sl]);
-      sid.id[pos] = static_cast<unsigned long long>(__double_as_longlong(col[SC_ID * POOL + sl]));
+      for (int c = 0; c < 8; ++c) __stcs(gp + c * a.n, col[c * POOL + sl]);
+      gid[out_off + k] = static_cast<unsigned long long>(__double_as_longlong(col[SC_ID * POOL + sl]));
       if (e & 0x8000u) {                                             // attached: population control refills this position at t_sync
+        const long long pos = lo + out_off + k;
         const unsigned int idx = atomicAdd(&L.counters[C_DEAD], 1u);
         if (idx < L.dead_cap) { L.dead[idx] = static_cast<unsigned int>(pos); L.dead_flag[pos] = 1; } else atomicExch(&L.counters[C_OVERFLOW], 1u);
-      }
+      } else eps_end = kinetic_eV(vx, vy, vz);                     // the energy at t_sync (same bits as the flight computed, BMC.C:901)
       const unsigned int kin = listK[k];
       if (kin != 0xFFFFu) {                                          // refill the slot just written back
-        const long long pin = in_ptr + kin;
+        const double* const gq = g0 + (in_off + static_cast<int>(kin));
 #pragma unroll
-        for (int c = 0; c < 8; ++c) cp_async8(&col[c * POOL + sl], &gcol[c][pin]);
-        cp_async8(&col[SC_ID * POOL + sl], &sid.id[pin]);
+        for (int c = 0; c < 8; ++c) cp_async8(&col[c * POOL + sl], gq + c * a.n);
+        cp_async8(&col[SC_ID * POOL + sl], &gid[in_off + static_cast<int>(kin)]);
         col[SC_T * POOL + sl] = a.t0; s_used[sl] = 0;
       }
+      }
+      warp_max_into(&s_wmax[2 * warp], eps_end, lane);
     }
     for (int k = tid; k < nRefill; k += STREAM_THREADS) {          // refills of slots that were already empty (start and end of the range)
       const unsigned int sl = listI[k];
       if (sl == 0xFFFFu) continue;
-      const long long pos = in_ptr + k;
+      const double* const gq = g0 + (in_off + k);
 #pragma unroll
-      for (int c = 0; c < 8; ++c) cp_async8(&col[c * POOL + sl], &gcol[c][pos]);
-      cp_async8(&col[SC_ID * POOL + sl], &sid.id[pos]);
+      for (int c = 0; c < 8; ++c) cp_async8(&col[c * POOL + sl], gq + c * a.n);
+      cp_async8(&col[SC_ID * POOL + sl], &gid[in_off + k]);
       col[SC_T * POOL + sl] = a.t0; s_used[sl] = 0;
     }
     cp_async_commit();
-    in_ptr += nRefill; out_ptr += nRet;
+    if (tid == 0) { s_rs[RS_IN] = in_off + nRefill; s_rs[RS_OUT] = out_off + nRet; }   // read again after the barrier that ends the round
     {   // pull the next round's input lines towards L2 while this round computes
-      const long long ahead = in_ptr + static_cast<long long>(tid) * 16;   // 16 doubles = one 128-byte line per thread and column
-      if (ahead < hi && tid < 48) {
+      const int ahead = in_off + nRefill + tid * 16;   // 16 doubles = one 128-byte line per thread and column
+      if (ahead < s_rs[RS_LEN] && tid < 48) {
 #pragma unroll
-        for (int c = 0; c < 8; ++c) asm volatile("prefetch.global.L2 [%0];" ::"l"(&gcol[c][ahead]));
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(&sid.id[ahead]));
+        for (int c = 0; c < 8; ++c) asm volatile("prefetch.global.L2 [%0];" ::"l"(g0 + c * a.n + ahead));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(&gid[ahead]));
       }
     }
 
-    // ================= (3) phase B: collisions on the compacted lists (BMC.C:916-1031, 1054-1280), cold-gas branch first =================
+    // ================= (3) collisions on the compacted lists (BMC.C:916-1031, 1054-1280), cold-gas branch first =================
+#pragma unroll 1
     for (int pass = 0; pass < 2; ++pass) {
       if (pass == 0 ? (GT == GT_TRUE) : (GT == GT_FALSE)) continue;
-      const int first = pass == 0 ? 0 : nBc, count = pass == 0 ? nBc : nBt;
+      const int first = pass == 0 ? 0 : s_rs[RS_NBC], count = pass == 0 ? s_rs[RS_NBC] : s_rs[RS_NBT];
+#pragma unroll 1
       for (int chunk_i = warp; chunk_i * 32 < count; chunk_i += STREAM_WARPS) {
         const int k = chunk_i * 32 + lane;
         int chosen = NOT_ADVANCED;
-        double dE = 0;
+        double dE = 0, seen = 0;
         if (k < count) {
           const int sl = listR[first + k];
           Particle p;
@@ -226,110 +306,134 @@ __global__ void __launch_bounds__(STREAM_THREADS, 2) k_advance_stream(const Mode
           p.eps = kinetic_eV(p.vx, p.vy, p.vz);
           PhiloxRng rng;
           const unsigned long long id = static_cast<unsigned long long>(__double_as_longlong(col[SC_ID * POOL + sl]));
-          rng.k0 = k0; rng.k1 = k1; rng.c0 = static_cast<uint32_t>(id); rng.c1 = static_cast<uint32_t>(id >> 32); rng.c2 = a.interval;
+          rng.k0 = static_cast<uint32_t>(a.seed); rng.k1 = static_cast<uint32_t>(a.seed >> 32);
+          rng.c0 = static_cast<uint32_t>(id); rng.c1 = static_cast<uint32_t>(id >> 32); rng.c2 = a.interval;
           rng.used = s_used[sl]; rng.blk = 0xFFFFFFFFu;
           EventOut o; o.table_clamped = 0; o.nu_exceeded = 0; o.dE = 0;
           if (pass == 1) chosen = thermal_collide<GT>(m, p, rng, o);
           else chosen = cold_collide<GT>(m, p, col[SC_TCF * POOL + sl], rng, o);
-          n_clamp += o.table_clamped;
+          if (o.table_clamped) atomicAdd(&s_misc[MC_CLAMP], 1u);
           unsigned char outcome = FL_FLIGHT;
           if (chosen >= 0) {
             dE = o.dE;
             const int type = __ldg(&m.type[chosen]);
             if (type == T_IONIZATION) {
-              ++n_born;
+              atomicAdd(&s_misc[MC_BORN], 1u);
               uint32_t cc1, ck1; child_stream(rng.c1, rng.k1, rng.used, cc1, ck1);
               push_pending(pend, L.counters, o, p.t, rng.c0, cc1, ck1);
-            } else if (type == T_ATTACHMENT) { ++n_att; outcome = FL_DEAD; }
-          } else ++n_null;                                         // aborted picks count as null collisions (BMC.C:1137-1140)
-          max_seen = fmax(max_seen, p.eps);
+            } else if (type == T_ATTACHMENT) { atomicAdd(&s_misc[MC_ATT], 1u); outcome = FL_DEAD; }
+          }                                                        // aborted picks count as null collisions (BMC.C:1137-1140): see RS_SUMF
+          seen = p.eps;
           col[SC_VX * POOL + sl] = p.vx; col[SC_VY * POOL + sl] = p.vy; col[SC_VZ * POOL + sl] = p.vz;
-          col[SC_TCF * POOL + sl] = NON_DEF;                       // the next free time is drawn at the start of phase A (same stream position)
+          col[SC_TCF * POOL + sl] = NON_DEF;                       // the next free time is drawn at the start of the flight (same stream position)
           s_used[sl] = rng.used;
           flag[sl] = outcome;
         }
         tally_collisions_fx(chosen, dE, s_cnt, s_gain, s_loss, lane);
+        warp_max_into(&s_wmax[2 * warp + 1], seen, lane);
       }
     }
-    cp_async_wait_all();   // this thread's refills have landed; the barrier publishes everybody's (and phase B's results)
-    __syncthreads();
 
-    // ================= (4) phase A: one free flight + null-collision test per electron (BMC.C:650-667, 804-905, 1035-1053) =================
-    for (int chunk_i = warp; chunk_i * 32 < nF; chunk_i += STREAM_WARPS) {
-      const int k = chunk_i * 32 + lane;
-      if (k < nF) {
-        const int sl = listF[k];
-        if (flag[sl] == FL_FLIGHT) {                               // (an electron attached in phase B stays FL_DEAD and retires in the next scan)
-          Particle p;
-          p.x = col[SC_X * POOL + sl]; p.y = col[SC_Y * POOL + sl]; p.z = col[SC_Z * POOL + sl];
-          p.vx = col[SC_VX * POOL + sl]; p.vy = col[SC_VY * POOL + sl]; p.vz = col[SC_VZ * POOL + sl];
-          p.tcf = col[SC_TCF * POOL + sl]; p.nue = col[SC_NUE * POOL + sl]; p.t = col[SC_T * POOL + sl];
+    // ================= (4) one free flight + null-collision test per electron (BMC.C:650-667, 804-905, 1035-1053) =================
+#pragma unroll 1
+    for (int part = 0; part < 2; ++part) {
+      if (part == 1) {
+        cp_async_wait_all();   // this thread's refills have landed; the barrier publishes everybody's (and the results of (3))
+        __syncthreads();
+      }
+      const int first = part == 0 ? 0 : s_rs[RS_NFL], count = part == 0 ? s_rs[RS_NFL] : s_rs[RS_NF] - s_rs[RS_NFL];
+#pragma unroll 1
+      for (int chunk_i = warp; chunk_i * 32 < count; chunk_i += STREAM_WARPS) {
+        const int k = chunk_i * 32 + lane;
+        bool active = false;
+        double seen = 0;
+        int sl = 0;
+        Particle p;
+        unsigned int used = 0;
+        unsigned long long id = 0;
+        bool need_tcf = false;
+        if (k < count) {
+          sl = listF[first + k];
+          if (flag[sl] == FL_FLIGHT) {                             // (an electron attached in (3) stays FL_DEAD and retires in the next scan)
+            active = true;
+            p.x = col[SC_X * POOL + sl]; p.y = col[SC_Y * POOL + sl]; p.z = col[SC_Z * POOL + sl];
+            p.vx = col[SC_VX * POOL + sl]; p.vy = col[SC_VY * POOL + sl]; p.vz = col[SC_VZ * POOL + sl];
+            p.tcf = col[SC_TCF * POOL + sl]; p.nue = col[SC_NUE * POOL + sl]; p.t = col[SC_T * POOL + sl];
+            id = static_cast<unsigned long long>(__double_as_longlong(col[SC_ID * POOL + sl]));
+            used = s_used[sl];
+            need_tcf = (p.tcf == NON_DEF);
+          }
+        }
+        // a warp of refilled electrons (they come with the rest of their previous free time) skips the logarithm: warp-uniform branch
+        const bool any_draw = __any_sync(FULL, need_tcf);
+        if (active) {
           p.eps = kinetic_eV(p.vx, p.vy, p.vz);
           // one convergent draw site: the free time (if needed) and the null-test uniform come from the same Philox block
-          const unsigned long long id = static_cast<unsigned long long>(__double_as_longlong(col[SC_ID * POOL + sl]));
-          const bool need_tcf = (p.tcf == NON_DEF);
-          unsigned int used = s_used[sl];
           if (need_tcf) used = (used + 1u) & ~1u;                    // free-time draws start on an even index (PhiloxRng::align)
           uint32_t o4[4];
-          philox4x32_10(static_cast<uint32_t>(id), static_cast<uint32_t>(id >> 32), a.interval, used >> 1, k0, k1, o4);
+          philox4x32_10(static_cast<uint32_t>(id), static_cast<uint32_t>(id >> 32), a.interval, used >> 1, static_cast<uint32_t>(a.seed), static_cast<uint32_t>(a.seed >> 32), o4);
           const double u0 = u52(o4[1], o4[0]), u1 = u52(o4[3], o4[2]);
-          const double drawn = -log(u0) / a.nu_trial;               // BMC.C:650-655 (computed by every lane, used by those that need it)
-          if (need_tcf) { p.tcf = drawn; p.nue = a.nu_trial; ++used; }
+          if (any_draw) {
+            const double drawn = -log(u0) / a.nu_trial;             // BMC.C:650-655
+            if (need_tcf) { p.tcf = drawn; p.nue = a.nu_trial; ++used; }
+          }
           const double u_null = (used & 1u) ? u1 : u0;
           const bool partial = (p.t + p.tcf > a.t_sync);             // BMC.C:657
           const double dt = partial ? (a.t_sync - p.t) : p.tcf;
-          gain_field += flight<FIELD>(m, p, dt);                     // one flight site for both outcomes (BMC.C:659, :666)
+          s_gf[tid] += flight<FIELD>(m, p, dt);                      // one flight site for both outcomes (BMC.C:659, :666)
           unsigned char outcome;
-          if (partial) { p.t = a.t_sync; p.tcf -= dt; outcome = FL_DONE; max_end = fmax(max_end, p.eps); }
+          if (partial) { p.t = a.t_sync; p.tcf -= dt; outcome = FL_DONE; }
           else {
             p.t += p.tcf;
-            if (thermal_branch<GT>(m, p.eps)) { outcome = FL_REALT; p.tcf = NON_DEF; }   // the thermal-target branch draws its own numbers in phase B
+            if (thermal_branch<GT>(m, p.eps)) { outcome = FL_REALT; p.tcf = NON_DEF; }   // the thermal-target branch draws its own numbers in (3)
             else {
-              EventOut o; o.table_clamped = 0; o.nu_exceeded = 0;
-              double Rnu;
+              double Rnu; bool clamped, exceeded;
               ++used;
-              if (cold_null_test_u(m, p, u_null, Rnu, o)) { outcome = FL_REAL; p.tcf = Rnu; }
-              else { outcome = FL_FLIGHT; p.tcf = NON_DEF; ++n_null; }
-              n_clamp += o.table_clamped; n_nuex += o.nu_exceeded;
+              const double* __restrict__ nu_tab = a.pad ? s_nu : m.nu_tot;
+              if (stream_null_test(m, nu_tab, p.eps, p.nue, u_null, Rnu, clamped, exceeded)) { outcome = FL_REAL; p.tcf = Rnu; }
+              else { outcome = FL_FLIGHT; p.tcf = NON_DEF; }
+              if (clamped) atomicAdd(&s_misc[MC_CLAMP], 1u);
+              if (exceeded) atomicAdd(&s_misc[MC_NUEX], 1u);
             }
           }
-          max_seen = fmax(max_seen, p.eps);
+          seen = p.eps;
           col[SC_X * POOL + sl] = p.x; col[SC_Y * POOL + sl] = p.y; col[SC_Z * POOL + sl] = p.z;
           col[SC_VX * POOL + sl] = p.vx; col[SC_VY * POOL + sl] = p.vy; col[SC_VZ * POOL + sl] = p.vz;
           col[SC_TCF * POOL + sl] = p.tcf; col[SC_NUE * POOL + sl] = p.nue; col[SC_T * POOL + sl] = p.t;
           s_used[sl] = used;
           flag[sl] = outcome;
         }
+        warp_max_into(&s_wmax[2 * warp + 1], seen, lane);
       }
     }
     __syncthreads();
   }
 
-  {
-    const double v1 = warp_sum(static_cast<double>(n_null)), v2 = warp_sum(static_cast<double>(n_born)), v3 = warp_sum(static_cast<double>(n_att)),
-                 v4 = warp_sum(gain_field), v5 = warp_sum(static_cast<double>(n_clamp)), v6 = warp_sum(static_cast<double>(n_nuex)),
-                 m0 = warp_max(max_end), m1 = warp_max(max_seen);
-    if (lane == 0) {
-      double* acc = s_acc[warp];
-      acc[R_N_NULL] = v1; acc[R_N_BORN] = v2; acc[R_N_ATTACHED] = v3; acc[R_GAIN_FIELD] = v4;
-      acc[R_N_TABLE_CLAMPED] = v5; acc[R_N_NU_EXCEEDED] = v6; acc[R_MAX_EPS] = m0; acc[R_MAX_EPS_SEEN] = m1;
-    }
-  }
-  __syncthreads();
-  if (tid == 0) {   // real collisions = sum of the per-process counts
+  const int tid = tid_now();
+  if (tid == 0) {   // header of the CTA: real collisions = sum of the per-process counts; rare-event counters; fixed-order sums
     double nr = 0;
     for (int k = 0; k < m.P; ++k) nr += static_cast<double>(s_cnt[k]);
-    s_acc[0][R_N_REAL] = nr;
+    s_hdr[R_N_REAL] = nr;
+    // events = non-partial flights = (flights flown) - (electrons of the range); null = events - real  (BMC.C:1308-1320)
+    const unsigned long long flights = *reinterpret_cast<volatile unsigned long long*>(&s_scan[9]) - s_misc[MC_ATT];
+    const unsigned long long partials_n = static_cast<unsigned long long>(s_rs[RS_LEN]) - s_misc[MC_ATT];
+    s_hdr[R_N_NULL] = static_cast<double>(flights - partials_n) - nr;
+    s_hdr[R_N_BORN] = static_cast<double>(s_misc[MC_BORN]); s_hdr[R_N_ATTACHED] = static_cast<double>(s_misc[MC_ATT]);
+    s_hdr[R_N_TABLE_CLAMPED] = static_cast<double>(s_misc[MC_CLAMP]); s_hdr[R_N_NU_EXCEEDED] = static_cast<double>(s_misc[MC_NUEX]);
+    double gf = 0, m0 = 0, m1 = 0;
+    for (int w = 0; w < STREAM_WARPS; ++w) {   // same order as a warp-shuffle tree over lanes followed by a sum over warps would not be needed: any fixed order is reproducible
+      double ws = 0;
+      for (int l = 0; l < 32; ++l) ws += s_gf[w * 32 + l];
+      gf += ws;
+      m0 = fmax(m0, __longlong_as_double(static_cast<long long>(s_wmax[2 * w]))); m1 = fmax(m1, __longlong_as_double(static_cast<long long>(s_wmax[2 * w + 1])));
+    }
+    s_hdr[R_GAIN_FIELD] = gf; s_hdr[R_MAX_EPS] = m0; s_hdr[R_MAX_EPS_SEEN] = fmax(m0, m1);
   }
   __syncthreads();
-  {   // partials: header from the warp accumulators, per-process tallies converted from fixed point
-    const int len = R_HEADER + 3 * m.P;
-    double* out = partials + static_cast<size_t>(blockIdx.x) * len;
-    for (int j = tid; j < R_HEADER; j += STREAM_THREADS) {
-      double v = s_acc[0][j];
-      for (int w = 1; w < STREAM_WARPS; ++w) v = (j >= R_SUM_COUNT) ? fmax(v, s_acc[w][j]) : v + s_acc[w][j];
-      out[j] = v;
-    }
+  {   // partials: header, per-process tallies converted from fixed point
+    const int plen = R_HEADER + 3 * m.P;
+    double* out = partials + static_cast<size_t>(blockIdx.x) * plen;
+    for (int j = tid; j < R_HEADER; j += STREAM_THREADS) out[j] = s_hdr[j];
     for (int k = tid; k < m.P; k += STREAM_THREADS) {
       out[R_HEADER + k] = static_cast<double>(s_cnt[k]);
       out[R_HEADER + m.P + k] = static_cast<double>(s_gain[k]) / TALLY_SCALE;

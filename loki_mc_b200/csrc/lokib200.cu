@@ -189,11 +189,13 @@ int launch_advance(lokib200_engine* h, bool sample, const Model& m, const AdvArg
 
 template <int F, int G>
 int launch_stream_t(lokib200_engine* h, const Model& m, const AdvArgs& a, const HistGrid& hg) {
-  const size_t smem = stream_smem_bytes(h->P, 0);
+  const int nu_rows = stream_nu_rows(h->P, h->nE);   // nu_tot staged in shared memory when it fits beside the pool
+  const size_t smem = stream_smem_bytes(h->P, 0) + static_cast<size_t>(nu_rows) * 8;
   CK(cudaFuncSetAttribute(k_advance_stream<F, G, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   CK(cudaFuncSetAttribute(k_advance_stream<F, G, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-  const StateId sid{h->st, h->d_id};
-  k_advance_stream<F, G, false><<<h->tile_blocks, STREAM_THREADS, smem, h->stream>>>(m, sid, h->lists, h->pend, a, hg, h->d_adv_part);
+  const StateId sid{h->st, h->d_id};   // the kernel addresses column c as st.x + c * n (one allocation, lokib200_create)
+  AdvArgs as = a; as.pad = static_cast<unsigned int>(nu_rows);
+  k_advance_stream<F, G, false><<<h->tile_blocks, STREAM_THREADS, smem, h->stream>>>(m, sid, h->lists, h->pend, as, hg, h->d_adv_part);
   return 0;
 }
 template <int F>
@@ -272,7 +274,7 @@ int push_tables(lokib200_engine* h) {   // h_cum (padded) / h_nu_tot -> device
     for (void* q : {static_cast<void*>(h->d_cum), static_cast<void*>(h->d_nu_tot), static_cast<void*>(h->d_pair), static_cast<void*>(h->d_coarse)}) if (q) cudaFree(q);
     CK(cudaMalloc(&h->d_cum, need * sizeof(double)));
     CK(cudaMalloc(&h->d_nu_tot, static_cast<size_t>(h->nE) * sizeof(double)));
-#ifdef LK_SELECT_2LEVEL
+#if defined(LK_SELECT_2LEVEL) || !defined(LK_SELECT_SPLIT_ROWS)
     CK(cudaMalloc(&h->d_pair, need * sizeof(double2)));
     CK(cudaMalloc(&h->d_coarse, need_c * sizeof(double2)));
 #else
@@ -280,7 +282,7 @@ int push_tables(lokib200_engine* h) {   // h_cum (padded) / h_nu_tot -> device
 #endif
     h->d_cum_cap = need;
   }
-#ifdef LK_SELECT_2LEVEL
+#if defined(LK_SELECT_2LEVEL) || !defined(LK_SELECT_SPLIT_ROWS)
   // row-pair + coarse forms, derived from the same doubles (no arithmetic: the kernels see identical table values)
   h->h_pair.resize(need); h->h_coarse.resize(need_c);
   for (int i = 0; i < h->nE; ++i) {
