@@ -117,6 +117,16 @@ __device__ __forceinline__ void warp_max_into(unsigned long long* slot, double v
   if (lane == 0) { const unsigned long long mx = (static_cast<unsigned long long>(mh) << 32) | ml; if (mx > *slot) *slot = mx; }
 }
 
+struct Flyer {   // one electron in the flight phase (two per lane)
+  Particle p;
+  unsigned long long id;
+  double gain;
+  unsigned int used;
+  int sl;
+  unsigned char outcome;
+  bool active, need, clamped, exceeded;
+};
+
 enum : int { MC_BORN = 0, MC_ATT, MC_CLAMP, MC_NUEX, MC_COUNT };   // rare events: counted with shared atomics, not in registers
 // CTA-uniform state of a round lives in shared memory and is re-read where it is used: with 128 registers per thread every value that stays
 // live across the inlined collision code is a spill candidate, and local-memory spills miss the small L1 (profiles/r1_v10_*)
@@ -335,6 +345,9 @@ __global__ void __launch_bounds__(STREAM_THREADS, 2) k_advance_stream(const Mode
     }
 
     // ================= (4) one free flight + null-collision test per electron (BMC.C:650-667, 804-905, 1035-1053) =================
+    // Two electrons per lane (k and k + 32 of a 64-wide chunk), advanced side by side through one branch-free block: with four warps per
+    // scheduler the dependent chains of a single electron (ten Philox rounds, the logarithm, the interpolated table test) leave the issue
+    // slots idle two cycles out of three; two independent chains in the same basic block let ptxas interleave them.
 #pragma unroll 1
     for (int part = 0; part < 2; ++part) {
       if (part == 1) {
@@ -342,66 +355,87 @@ __global__ void __launch_bounds__(STREAM_THREADS, 2) k_advance_stream(const Mode
         __syncthreads();
       }
       const int first = part == 0 ? 0 : s_rs[RS_NFL], count = part == 0 ? s_rs[RS_NFL] : s_rs[RS_NF] - s_rs[RS_NFL];
+      const double* __restrict__ nu_tab = a.pad ? s_nu : m.nu_tot;
+      const double rnu = recip_for_div(a.nu_trial);
 #pragma unroll 1
-      for (int chunk_i = warp; chunk_i * 32 < count; chunk_i += STREAM_WARPS) {
-        const int k = chunk_i * 32 + lane;
-        bool active = false;
-        double seen = 0;
-        int sl = 0;
-        Particle p;
-        unsigned int used = 0;
-        unsigned long long id = 0;
-        bool need_tcf = false;
-        if (k < count) {
-          sl = listF[first + k];
-          if (flag[sl] == FL_FLIGHT) {                             // (an electron attached in (3) stays FL_DEAD and retires in the next scan)
-            active = true;
-            p.x = col[SC_X * POOL + sl]; p.y = col[SC_Y * POOL + sl]; p.z = col[SC_Z * POOL + sl];
-            p.vx = col[SC_VX * POOL + sl]; p.vy = col[SC_VY * POOL + sl]; p.vz = col[SC_VZ * POOL + sl];
-            p.tcf = col[SC_TCF * POOL + sl]; p.nue = col[SC_NUE * POOL + sl]; p.t = col[SC_T * POOL + sl];
-            id = static_cast<unsigned long long>(__double_as_longlong(col[SC_ID * POOL + sl]));
-            used = s_used[sl];
-            need_tcf = (p.tcf == NON_DEF);
-          }
+      for (int base = warp * 64; base < count; base += STREAM_WARPS * 64) {
+        Flyer e[2];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const int k = base + 32 * j + lane;
+          Flyer& f = e[j];
+          f.sl = (k < count) ? listF[first + k] : 0;
+        }
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          Flyer& f = e[j];
+          const int k = base + 32 * j + lane, sl = f.sl;
+          f.active = (k < count) && (flag[sl] == FL_FLIGHT);       // (an electron attached in (3) stays FL_DEAD and retires in the next scan)
+          f.p.x = col[SC_X * POOL + sl]; f.p.y = col[SC_Y * POOL + sl]; f.p.z = col[SC_Z * POOL + sl];
+          f.p.vx = col[SC_VX * POOL + sl]; f.p.vy = col[SC_VY * POOL + sl]; f.p.vz = col[SC_VZ * POOL + sl];
+          f.p.tcf = col[SC_TCF * POOL + sl]; f.p.nue = col[SC_NUE * POOL + sl]; f.p.t = col[SC_T * POOL + sl];
+          f.id = static_cast<unsigned long long>(__double_as_longlong(col[SC_ID * POOL + sl]));
+          f.used = s_used[sl];
+          f.need = f.active && (f.p.tcf == NON_DEF);
+          if (f.need) f.used = (f.used + 1u) & ~1u;                 // free-time draws start on an even index (PhiloxRng::align)
         }
         // a warp of refilled electrons (they come with the rest of their previous free time) skips the logarithm: warp-uniform branch
-        const bool any_draw = __any_sync(FULL, need_tcf);
-        if (active) {
-          p.eps = kinetic_eV(p.vx, p.vy, p.vz);
-          // one convergent draw site: the free time (if needed) and the null-test uniform come from the same Philox block
-          if (need_tcf) used = (used + 1u) & ~1u;                    // free-time draws start on an even index (PhiloxRng::align)
+        const bool any_draw = __any_sync(FULL, e[0].need || e[1].need);
+        double u0[2], u1[2];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {   // one convergent draw site: the free time (if needed) and the null-test uniform come from the same Philox block
           uint32_t o4[4];
-          philox4x32_10(static_cast<uint32_t>(id), static_cast<uint32_t>(id >> 32), a.interval, used >> 1, static_cast<uint32_t>(a.seed), static_cast<uint32_t>(a.seed >> 32), o4);
-          const double u0 = u52(o4[1], o4[0]), u1 = u52(o4[3], o4[2]);
-          if (any_draw) {
-            const double drawn = -log(u0) / a.nu_trial;             // BMC.C:650-655
-            if (need_tcf) { p.tcf = drawn; p.nue = a.nu_trial; ++used; }
+          philox4x32_10(static_cast<uint32_t>(e[j].id), static_cast<uint32_t>(e[j].id >> 32), a.interval, e[j].used >> 1, static_cast<uint32_t>(a.seed),
+                        static_cast<uint32_t>(a.seed >> 32), o4);
+          u0[j] = u52(o4[1], o4[0]); u1[j] = u52(o4[3], o4[2]);
+        }
+        if (any_draw) {
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            const double drawn = div_by(-log_normal(u0[j]), a.nu_trial, rnu);   // -log(u) / nu_trial, BMC.C:650-655
+            if (e[j].need) { e[j].p.tcf = drawn; e[j].p.nue = a.nu_trial; ++e[j].used; }
           }
-          const double u_null = (used & 1u) ? u1 : u0;
+        }
+        double seen = 0;
+        bool rare = false;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          Flyer& f = e[j];
+          Particle& p = f.p;
+          p.eps = kinetic_eV(p.vx, p.vy, p.vz);
+          const double u_null = (f.used & 1u) ? u1[j] : u0[j];
           const bool partial = (p.t + p.tcf > a.t_sync);             // BMC.C:657
           const double dt = partial ? (a.t_sync - p.t) : p.tcf;
-          s_gf[tid] += flight<FIELD>(m, p, dt);                      // one flight site for both outcomes (BMC.C:659, :666)
-          unsigned char outcome;
-          if (partial) { p.t = a.t_sync; p.tcf -= dt; outcome = FL_DONE; }
-          else {
-            p.t += p.tcf;
-            if (thermal_branch<GT>(m, p.eps)) { outcome = FL_REALT; p.tcf = NON_DEF; }   // the thermal-target branch draws its own numbers in (3)
-            else {
-              double Rnu; bool clamped, exceeded;
-              ++used;
-              const double* __restrict__ nu_tab = a.pad ? s_nu : m.nu_tot;
-              if (stream_null_test(m, nu_tab, p.eps, p.nue, u_null, Rnu, clamped, exceeded)) { outcome = FL_REAL; p.tcf = Rnu; }
-              else { outcome = FL_FLIGHT; p.tcf = NON_DEF; }
-              if (clamped) atomicAdd(&s_misc[MC_CLAMP], 1u);
-              if (exceeded) atomicAdd(&s_misc[MC_NUEX], 1u);
-            }
+          f.gain = flight<FIELD>(m, p, dt);                          // one flight site for both outcomes (BMC.C:659, :666)
+          const bool thermal = thermal_branch<GT>(m, p.eps);
+          double Rnu; bool clamped, exceeded;
+          const bool real = stream_null_test(m, nu_tab, p.eps, p.nue, u_null, Rnu, clamped, exceeded);
+          const bool tested = !partial && !thermal;                  // the thermal-target branch draws its own numbers in (3)
+          f.outcome = partial ? FL_DONE : thermal ? FL_REALT : real ? FL_REAL : FL_FLIGHT;
+          const double t_event = p.t + p.tcf;
+          p.tcf = partial ? (p.tcf - dt) : (tested && real) ? Rnu : NON_DEF;
+          p.t = partial ? a.t_sync : t_event;
+          f.used += tested ? 1u : 0u;
+          f.clamped = f.active && tested && clamped; f.exceeded = f.active && tested && exceeded;
+          rare = rare || f.clamped || f.exceeded;
+          if (f.active) seen = fmax(seen, p.eps);
+        }
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const Flyer& f = e[j];
+          if (f.active) {
+            const int sl = f.sl;
+            s_gf[tid] += f.gain;
+            col[SC_X * POOL + sl] = f.p.x; col[SC_Y * POOL + sl] = f.p.y; col[SC_Z * POOL + sl] = f.p.z;
+            col[SC_VX * POOL + sl] = f.p.vx; col[SC_VY * POOL + sl] = f.p.vy; col[SC_VZ * POOL + sl] = f.p.vz;
+            col[SC_TCF * POOL + sl] = f.p.tcf; col[SC_NUE * POOL + sl] = f.p.nue; col[SC_T * POOL + sl] = f.p.t;
+            s_used[sl] = f.used;
+            flag[sl] = f.outcome;
           }
-          seen = p.eps;
-          col[SC_X * POOL + sl] = p.x; col[SC_Y * POOL + sl] = p.y; col[SC_Z * POOL + sl] = p.z;
-          col[SC_VX * POOL + sl] = p.vx; col[SC_VY * POOL + sl] = p.vy; col[SC_VZ * POOL + sl] = p.vz;
-          col[SC_TCF * POOL + sl] = p.tcf; col[SC_NUE * POOL + sl] = p.nue; col[SC_T * POOL + sl] = p.t;
-          s_used[sl] = used;
-          flag[sl] = outcome;
+        }
+        if (rare) {
+#pragma unroll
+          for (int j = 0; j < 2; ++j) { if (e[j].clamped) atomicAdd(&s_misc[MC_CLAMP], 1u); if (e[j].exceeded) atomicAdd(&s_misc[MC_NUEX], 1u); }
         }
         warp_max_into(&s_wmax[2 * warp + 1], seen, lane);
       }

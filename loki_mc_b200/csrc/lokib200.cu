@@ -14,7 +14,11 @@
 #include <string>
 #include <vector>
 
+#ifdef LK_STREAM_PREV
+#include "lk_stream_prev.cuh"
+#else
 #include "lk_stream.cuh"
+#endif
 
 using namespace lk;
 
