@@ -45,7 +45,7 @@ __host__ __device__ inline size_t stream_smem_bytes(int P, int nEn_hist) {
   b += static_cast<size_t>(POOL) * 4;                       // draw counters
   b += static_cast<size_t>(P) * 4;                          // counts
   b += static_cast<size_t>(nEn_hist) * 4;                   // energy histogram
-  b += static_cast<size_t>(POOL) * 2 * 5;                   // five lists
+  b += static_cast<size_t>(POOL) * 2 * 4;                   // four lists
   b += POOL;                                                // flags
   b += 32;                                                  // rare-event counters
   b += 64;                                                  // CTA-uniform round state (cursors, list lengths)
@@ -130,7 +130,7 @@ struct Flyer {   // one electron in the flight phase (two per lane)
 enum : int { MC_BORN = 0, MC_ATT, MC_CLAMP, MC_NUEX, MC_COUNT };   // rare events: counted with shared atomics, not in registers
 // CTA-uniform state of a round lives in shared memory and is re-read where it is used: with 128 registers per thread every value that stays
 // live across the inlined collision code is a spill candidate, and local-memory spills miss the small L1 (profiles/r1_v10_*)
-enum : int { RS_IN = 0, RS_OUT, RS_LEN, RS_NFL, RS_NBC, RS_NBT, RS_NF, RS_COUNT };   // (the 64-bit ones, range start and flight count, sit in s_scan[8], s_scan[9])
+enum : int { RS_IN = 0, RS_OUT, RS_LEN, RS_NFL, RS_NBC, RS_NBT, RS_NRET, RS_NREFILL, RS_COUNT };   // (the 64-bit ones, range start and flight count, sit in s_scan[8], s_scan[9])
 
 // Round structure (one CTA, 256 threads, POOL resident electrons):
 //   (1) block scan over the slot flags -> lists: F = [continuing | collided this round | refilled this round], R = [cold | thermal], O/K/I retire + refill
@@ -156,9 +156,8 @@ __global__ void __launch_bounds__(STREAM_THREADS, 2) k_advance_stream(const Mode
   unsigned short* listF = reinterpret_cast<unsigned short*>(s_cnt + m.P);                   // [POOL] flights of this round
   unsigned short* listR = listF + POOL;                                                     // [POOL] collisions of this round: cold first, thermal after
   unsigned short* listO = listR + POOL;                                                     // [POOL] slots retiring this round (output order; bit 15: attached)
-  unsigned short* listK = listO + POOL;                                                     // [POOL] input rank of a retiring slot refilled at once (0xFFFF: stays empty)
-  unsigned short* listI = listK + POOL;                                                     // [POOL] refilled slots that were already empty (0xFFFF: see listK)
-  unsigned char* flag = reinterpret_cast<unsigned char*>(listI + POOL);                     // [POOL]
+  unsigned short* listE = listO + POOL;                                                     // [POOL] empty slots, in slot order
+  unsigned char* flag = reinterpret_cast<unsigned char*>(listE + POOL);                     // [POOL]
   unsigned int* s_misc = reinterpret_cast<unsigned int*>(flag + POOL);                      // [MC_COUNT]
   volatile int* s_rs = reinterpret_cast<volatile int*>(s_misc + 8);                         // [RS_COUNT] round state
   const size_t fixed_bytes = stream_smem_bytes(m.P, 0);
@@ -190,15 +189,14 @@ __global__ void __launch_bounds__(STREAM_THREADS, 2) k_advance_stream(const Mode
     // ================= (1) block scan over the slot flags: build the lists of this round in slot order =================
     const int tid = tid_now(), lane = tid & 31, warp = tid >> 5;
     const unsigned int f4 = reinterpret_cast<const unsigned int*>(flag)[tid];
-    unsigned int cFl = 0, cRc = 0, cRt = 0, cRet = 0, cFree = 0;
+    unsigned int cFl = 0, cRc = 0, cRt = 0, cRet = 0, cEmp = 0;
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       const unsigned int f = (f4 >> (8 * q)) & 0xFFu;
-      cFl += (f == FL_FLIGHT); cRc += (f == FL_REAL); cRt += (f == FL_REALT); cRet += (f == FL_DONE || f == FL_DEAD);
-      cFree += (f == FL_EMPTY || f == FL_DONE || f == FL_DEAD);
+      cFl += (f == FL_FLIGHT); cRc += (f == FL_REAL); cRt += (f == FL_REALT); cRet += (f == FL_DONE || f == FL_DEAD); cEmp += (f == FL_EMPTY);
     }
     const unsigned long long mine = static_cast<unsigned long long>(cFl) | (static_cast<unsigned long long>(cRc) << 12) | (static_cast<unsigned long long>(cRt) << 24) |
-                                    (static_cast<unsigned long long>(cRet) << 36) | (static_cast<unsigned long long>(cFree) << 48);
+                                    (static_cast<unsigned long long>(cRet) << 36) | (static_cast<unsigned long long>(cEmp) << 48);
     unsigned long long incl = mine;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { const unsigned long long v = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += v; }
@@ -209,38 +207,37 @@ __global__ void __launch_bounds__(STREAM_THREADS, 2) k_advance_stream(const Mode
     for (int w = 0; w < STREAM_WARPS; ++w) { const unsigned long long v = s_scan[w]; total += v; if (w < warp) before += v; }
     const unsigned long long excl = before + incl - mine;
     const int nFl = static_cast<int>(total & 0xFFFu), nRc = static_cast<int>((total >> 12) & 0xFFFu), nRt = static_cast<int>((total >> 24) & 0xFFFu),
-              nRet = static_cast<int>((total >> 36) & 0xFFFu), nFree = static_cast<int>((total >> 48) & 0xFFFu);
+              nRet = static_cast<int>((total >> 36) & 0xFFFu), nEmp = static_cast<int>((total >> 48) & 0xFFFu);
     const int in_off = s_rs[RS_IN], out_off = s_rs[RS_OUT];
-    const int nRefill = min(nFree, s_rs[RS_LEN] - in_off);
+    // refill rank r: input element in_off + r goes to the r-th retiring slot (r < nRet), then to the empty slots in slot order
+    const int nRefill = min(nRet + nEmp, s_rs[RS_LEN] - in_off);
     // collisions are run in whole CTA-iterations; everything parked is flushed when the flights alone cannot keep the CTA busy
     const bool flush = (nFl + nRefill < STREAM_THREADS);
     const int nBc = flush ? nRc : (nRc / STREAM_THREADS) * STREAM_THREADS, nBt = flush ? nRt : (nRt / STREAM_THREADS) * STREAM_THREADS;
     int eFl = static_cast<int>(excl & 0xFFFu), eRc = static_cast<int>((excl >> 12) & 0xFFFu), eRt = static_cast<int>((excl >> 24) & 0xFFFu),
-        eRet = static_cast<int>((excl >> 36) & 0xFFFu), eFree = static_cast<int>((excl >> 48) & 0xFFFu);
-    const int baseC = nFl, baseT = nFl + nBc, baseI = nFl + nBc + nBt;   // F = [continuing | collided cold | collided thermal | refilled]
+        eRet = static_cast<int>((excl >> 36) & 0xFFFu), eEmp = static_cast<int>((excl >> 48) & 0xFFFu);
     unsigned int new_f4 = f4;
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       const int sl = tid * 4 + q;
       unsigned int f = (f4 >> (8 * q)) & 0xFFu;
-      const bool retiring = (f == FL_DONE || f == FL_DEAD);
-      if (retiring) {   // the thread that writes a slot back also issues its refill (program order, no barrier between the two)
+      if (f == FL_DONE || f == FL_DEAD) {
         listO[eRet] = static_cast<unsigned short>(sl | (f == FL_DEAD ? 0x8000 : 0));
-        listK[eRet] = (eFree < nRefill) ? static_cast<unsigned short>(eFree) : static_cast<unsigned short>(0xFFFF);
-        ++eRet; f = FL_EMPTY;
-      }
-      if (f == FL_EMPTY) {
-        if (eFree < nRefill) { listI[eFree] = retiring ? static_cast<unsigned short>(0xFFFF) : static_cast<unsigned short>(sl); listF[baseI + eFree] = static_cast<unsigned short>(sl); f = FL_FLIGHT; }
-        ++eFree;
+        f = (eRet < nRefill) ? FL_FLIGHT : FL_EMPTY;               // refilled by the thread that writes it back, flown by that thread
+        ++eRet;
+      } else if (f == FL_EMPTY) {
+        listE[eEmp] = static_cast<unsigned short>(sl);
+        if (nRet + eEmp < nRefill) f = FL_FLIGHT;
+        ++eEmp;
       } else if (f == FL_FLIGHT) { listF[eFl] = static_cast<unsigned short>(sl); ++eFl; }
-      else if (f == FL_REAL) { if (eRc < nBc) { listR[eRc] = static_cast<unsigned short>(sl); listF[baseC + eRc] = static_cast<unsigned short>(sl); } ++eRc; }
-      else if (f == FL_REALT) { if (eRt < nBt) { listR[nBc + eRt] = static_cast<unsigned short>(sl); listF[baseT + eRt] = static_cast<unsigned short>(sl); } ++eRt; }
+      else if (f == FL_REAL) { if (eRc < nBc) listR[eRc] = static_cast<unsigned short>(sl); ++eRc; }
+      else if (f == FL_REALT) { if (eRt < nBt) listR[nBc + eRt] = static_cast<unsigned short>(sl); ++eRt; }
       new_f4 = (new_f4 & ~(0xFFu << (8 * q))) | (f << (8 * q));
     }
     reinterpret_cast<unsigned int*>(flag)[tid] = new_f4;
     const int nF = nFl + nRefill + nBc + nBt;
     if (tid == 0) {   // every electron in F flies once this round unless it attaches in (3): sum of nF - electrons = non-partial flights = real + null events
-      s_rs[RS_NFL] = nFl; s_rs[RS_NBC] = nBc; s_rs[RS_NBT] = nBt; s_rs[RS_NF] = nF;
+      s_rs[RS_NFL] = nFl; s_rs[RS_NBC] = nBc; s_rs[RS_NBT] = nBt; s_rs[RS_NRET] = nRet; s_rs[RS_NREFILL] = nRefill;
       *reinterpret_cast<volatile unsigned long long*>(&s_scan[9]) += static_cast<unsigned long long>(nF);
     }
     __syncthreads();
@@ -249,42 +246,39 @@ __global__ void __launch_bounds__(STREAM_THREADS, 2) k_advance_stream(const Mode
     double* const g0 = sid.s.x + lo;
     unsigned long long* const gid = sid.id + lo;
 
-    // ================= (2) retire + refill, dense: electron k of the list <-> global element cursor + k =================
-    for (int kb = warp * 32; kb < nRet; kb += STREAM_THREADS) {
-      const int k = kb + lane;
-      double eps_end = 0;
-      if (k < nRet) {
-      const unsigned int e = listO[k];
-      const int sl = static_cast<int>(e & 0x7FFFu);
-      double* const gp = g0 + (out_off + k);
-      const double vx = col[SC_VX * POOL + sl], vy = col[SC_VY * POOL + sl], vz = col[SC_VZ * POOL + sl];
+    // ================= (2) retire + refill by rank: thread t owns ranks t, t + 256, ... =================
+    // rank r < nRet: the r-th retiring slot is written to output element out_off + r; rank r < nRefill: input element in_off + r is
+    // loaded into that same slot (or, past nRet, into an empty one).  One thread does both for a slot, in program order.
+    {
+      const int nOwn = max(nRet, nRefill);
+      for (int rb = warp * 32; rb < nOwn; rb += STREAM_THREADS) {
+        const int r = rb + lane;
+        double eps_end = 0;
+        if (r < nOwn) {
+          const unsigned int e = (r < nRet) ? listO[r] : listE[r - nRet];
+          const int sl = static_cast<int>(e & 0x7FFFu);
+          if (r < nRet) {
+            double* const gp = g0 + (out_off + r);
+            const double vx = col[SC_VX * POOL + sl], vy = col[SC_VY * POOL + sl], vz = col[SC_VZ * POOL + sl];
 #pragma unroll
-      for (int c = 0; c < 8; ++c) __stcs(gp + c * a.n, col[c * POOL + sl]);
-      gid[out_off + k] = static_cast<unsigned long long>(__double_as_longlong(col[SC_ID * POOL + sl]));
-      if (e & 0x8000u) {                                             // attached: population control refills this position at t_sync
-        const long long pos = lo + out_off + k;
-        const unsigned int idx = atomicAdd(&L.counters[C_DEAD], 1u);
-        if (idx < L.dead_cap) { L.dead[idx] = static_cast<unsigned int>(pos); L.dead_flag[pos] = 1; } else atomicExch(&L.counters[C_OVERFLOW], 1u);
-      } else eps_end = kinetic_eV(vx, vy, vz);                     // the energy at t_sync (same bits as the flight computed, BMC.C:901)
-      const unsigned int kin = listK[k];
-      if (kin != 0xFFFFu) {                                          // refill the slot just written back
-        const double* const gq = g0 + (in_off + static_cast<int>(kin));
+            for (int c = 0; c < 8; ++c) __stcs(gp + c * a.n, col[c * POOL + sl]);
+            gid[out_off + r] = static_cast<unsigned long long>(__double_as_longlong(col[SC_ID * POOL + sl]));
+            if (e & 0x8000u) {                                         // attached: population control refills this position at t_sync
+              const long long pos = lo + out_off + r;
+              const unsigned int idx = atomicAdd(&L.counters[C_DEAD], 1u);
+              if (idx < L.dead_cap) { L.dead[idx] = static_cast<unsigned int>(pos); L.dead_flag[pos] = 1; } else atomicExch(&L.counters[C_OVERFLOW], 1u);
+            } else eps_end = kinetic_eV(vx, vy, vz);                   // the energy at t_sync (same bits as the flight computed, BMC.C:901)
+          }
+          if (r < nRefill) {
+            const double* const gq = g0 + (in_off + r);
 #pragma unroll
-        for (int c = 0; c < 8; ++c) cp_async8(&col[c * POOL + sl], gq + c * a.n);
-        cp_async8(&col[SC_ID * POOL + sl], &gid[in_off + static_cast<int>(kin)]);
-        col[SC_T * POOL + sl] = a.t0; s_used[sl] = 0;
+            for (int c = 0; c < 8; ++c) cp_async8(&col[c * POOL + sl], gq + c * a.n);
+            cp_async8(&col[SC_ID * POOL + sl], &gid[in_off + r]);
+            col[SC_T * POOL + sl] = a.t0; s_used[sl] = 0;
+          }
+        }
+        warp_max_into(&s_wmax[2 * warp], eps_end, lane);
       }
-      }
-      warp_max_into(&s_wmax[2 * warp], eps_end, lane);
-    }
-    for (int k = tid; k < nRefill; k += STREAM_THREADS) {          // refills of slots that were already empty (start and end of the range)
-      const unsigned int sl = listI[k];
-      if (sl == 0xFFFFu) continue;
-      const double* const gq = g0 + (in_off + k);
-#pragma unroll
-      for (int c = 0; c < 8; ++c) cp_async8(&col[c * POOL + sl], gq + c * a.n);
-      cp_async8(&col[SC_ID * POOL + sl], &gid[in_off + k]);
-      col[SC_T * POOL + sl] = a.t0; s_used[sl] = 0;
     }
     cp_async_commit();
     if (tid == 0) { s_rs[RS_IN] = in_off + nRefill; s_rs[RS_OUT] = out_off + nRet; }   // read again after the barrier that ends the round
@@ -297,18 +291,18 @@ __global__ void __launch_bounds__(STREAM_THREADS, 2) k_advance_stream(const Mode
       }
     }
 
-    // ================= (3) collisions on the compacted lists (BMC.C:916-1031, 1054-1280), cold-gas branch first =================
+    // ================= (3) collisions on the compacted list (BMC.C:916-1031, 1054-1280): cold-gas entries first, thermal-target after =================
+    // chunk c belongs to warp c % 8, which also flies its electrons in (4): no CTA barrier between the two.  Both kinds share ONE
+    // instance of the collision dynamics (the process selection differs, the scattering code does not).
+    {
+      const int nBcr = s_rs[RS_NBC], nB = nBcr + s_rs[RS_NBT];
 #pragma unroll 1
-    for (int pass = 0; pass < 2; ++pass) {
-      if (pass == 0 ? (GT == GT_TRUE) : (GT == GT_FALSE)) continue;
-      const int first = pass == 0 ? 0 : s_rs[RS_NBC], count = pass == 0 ? s_rs[RS_NBC] : s_rs[RS_NBT];
-#pragma unroll 1
-      for (int chunk_i = warp; chunk_i * 32 < count; chunk_i += STREAM_WARPS) {
+      for (int chunk_i = warp; chunk_i * 32 < nB; chunk_i += STREAM_WARPS) {
         const int k = chunk_i * 32 + lane;
         int chosen = NOT_ADVANCED;
         double dE = 0, seen = 0;
-        if (k < count) {
-          const int sl = listR[first + k];
+        if (k < nB) {
+          const int sl = listR[k];
           Particle p;
           p.x = col[SC_X * POOL + sl]; p.y = col[SC_Y * POOL + sl]; p.z = col[SC_Z * POOL + sl];
           p.vx = col[SC_VX * POOL + sl]; p.vy = col[SC_VY * POOL + sl]; p.vz = col[SC_VZ * POOL + sl];
@@ -320,8 +314,10 @@ __global__ void __launch_bounds__(STREAM_THREADS, 2) k_advance_stream(const Mode
           rng.c0 = static_cast<uint32_t>(id); rng.c1 = static_cast<uint32_t>(id >> 32); rng.c2 = a.interval;
           rng.used = s_used[sl]; rng.blk = 0xFFFFFFFFu;
           EventOut o; o.table_clamped = 0; o.nu_exceeded = 0; o.dE = 0;
-          if (pass == 1) chosen = thermal_collide<GT>(m, p, rng, o);
-          else chosen = cold_collide<GT>(m, p, col[SC_TCF * POOL + sl], rng, o);
+          double Vx = 0, Vy = 0, Vz = 0;
+          if (GT != GT_FALSE && (GT == GT_TRUE || k >= nBcr)) chosen = thermal_select(m, p, rng, o, Vx, Vy, Vz);
+          else chosen = cold_select(m, p, col[SC_TCF * POOL + sl]);
+          if (chosen != NULL_COLLISION) chosen = collide_dynamics<GT>(m, chosen, p, Vx, Vy, Vz, rng, o);
           if (o.table_clamped) atomicAdd(&s_misc[MC_CLAMP], 1u);
           unsigned char outcome = FL_FLIGHT;
           if (chosen >= 0) {
@@ -332,7 +328,7 @@ __global__ void __launch_bounds__(STREAM_THREADS, 2) k_advance_stream(const Mode
               uint32_t cc1, ck1; child_stream(rng.c1, rng.k1, rng.used, cc1, ck1);
               push_pending(pend, L.counters, o, p.t, rng.c0, cc1, ck1);
             } else if (type == T_ATTACHMENT) { atomicAdd(&s_misc[MC_ATT], 1u); outcome = FL_DEAD; }
-          }                                                        // aborted picks count as null collisions (BMC.C:1137-1140): see RS_SUMF
+          }                                                        // aborted picks count as null collisions (BMC.C:1137-1140): see s_scan[9]
           seen = p.eps;
           col[SC_VX * POOL + sl] = p.vx; col[SC_VY * POOL + sl] = p.vy; col[SC_VZ * POOL + sl] = p.vz;
           col[SC_TCF * POOL + sl] = NON_DEF;                       // the next free time is drawn at the start of the flight (same stream position)
@@ -343,34 +339,40 @@ __global__ void __launch_bounds__(STREAM_THREADS, 2) k_advance_stream(const Mode
         warp_max_into(&s_wmax[2 * warp + 1], seen, lane);
       }
     }
+    __syncwarp();   // the warp's own collision results are visible to all its lanes
 
     // ================= (4) one free flight + null-collision test per electron (BMC.C:650-667, 804-905, 1035-1053) =================
-    // Two electrons per lane (k and k + 32 of a 64-wide chunk), advanced side by side through one branch-free block: with four warps per
-    // scheduler the dependent chains of a single electron (ten Philox rounds, the logarithm, the interpolated table test) leave the issue
-    // slots idle two cycles out of three; two independent chains in the same basic block let ptxas interleave them.
-#pragma unroll 1
-    for (int part = 0; part < 2; ++part) {
-      if (part == 1) {
-        cp_async_wait_all();   // this thread's refills have landed; the barrier publishes everybody's (and the results of (3))
-        __syncthreads();
-      }
-      const int first = part == 0 ? 0 : s_rs[RS_NFL], count = part == 0 ? s_rs[RS_NFL] : s_rs[RS_NF] - s_rs[RS_NFL];
+    // Two electrons per lane, advanced side by side through one branch-free block: with four warps per scheduler the dependent chains
+    // of a single electron (ten Philox rounds, the logarithm, the interpolated table test) leave the issue slots idle two cycles out of
+    // three; two independent chains in the same basic block let ptxas interleave them.
+    // A warp's work items, in order: the chunks it collided in (3), its share of the continuing electrons (chunk c of listF belongs to
+    // warp (c + rot) % 8), and -- after its own cp.async copies have landed -- the electrons it refilled in (2).  Nothing in this list
+    // was written by another warp in this round, so the round needs no barrier before its end.
+    {
+      const int nFlr = s_rs[RS_NFL], nB = s_rs[RS_NBC] + s_rs[RS_NBT], nRetr = s_rs[RS_NRET], nRefr = s_rs[RS_NREFILL];
+      const int kc = (nB + 31) >> 5, cc = (nFlr + 31) >> 5, rc = (nRefr + 31) >> 5;                // 32-wide chunks: collided, continuing, refilled
+      const int nK = (kc - warp + STREAM_WARPS - 1) >> 3;                                          // this warp's collided chunks (warp, warp + 8, ...)
+      const int wrot = (warp + kc) & (STREAM_WARPS - 1);                                           // continuing chunk c -> warp (c - kc) mod 8: evens out the totals
+      const int nC = (cc - wrot + STREAM_WARPS - 1) >> 3;
+      const int nR = (rc - warp + STREAM_WARPS - 1) >> 3;                                          // refill ranks [32 g, 32 g + 32), g = warp, warp + 8, ...: issued by these very threads
+      const int nA = nK + nC, nItems = nA + nR;
       const double* __restrict__ nu_tab = a.pad ? s_nu : m.nu_tot;
       const double rnu = recip_for_div(a.nu_trial);
+      bool waited = false;
 #pragma unroll 1
-      for (int base = warp * 64; base < count; base += STREAM_WARPS * 64) {
+      for (int it = 0; 2 * it < nItems; ++it) {
+        if (!waited && 2 * it + 1 >= nA) { cp_async_wait_all(); waited = true; }   // this pair holds a refilled chunk: this thread's copies have landed (only it reads them)
         Flyer e[2];
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
-          const int k = base + 32 * j + lane;
           Flyer& f = e[j];
-          f.sl = (k < count) ? listF[first + k] : 0;
-        }
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          Flyer& f = e[j];
-          const int k = base + 32 * j + lane, sl = f.sl;
-          f.active = (k < count) && (flag[sl] == FL_FLIGHT);       // (an electron attached in (3) stays FL_DEAD and retires in the next scan)
+          int sl = 0; bool act = false;
+          const int item = 2 * it + j;
+          if (item < nK) { const int k = 32 * (warp + 8 * item) + lane; if (k < nB) { sl = listR[k]; act = true; } }
+          else if (item < nA) { const int k = 32 * (wrot + 8 * (item - nK)) + lane; if (k < nFlr) { sl = listF[k]; act = true; } }
+          else if (item < nItems) { const int r = 32 * (warp + 8 * (item - nA)) + lane; if (r < nRefr) { sl = (r < nRetr) ? (listO[r] & 0x7FFF) : listE[r - nRetr]; act = true; } }
+          f.sl = sl;
+          f.active = act && (flag[sl] == FL_FLIGHT);                // (an electron attached in (3) stays FL_DEAD and retires in the next scan)
           f.p.x = col[SC_X * POOL + sl]; f.p.y = col[SC_Y * POOL + sl]; f.p.z = col[SC_Z * POOL + sl];
           f.p.vx = col[SC_VX * POOL + sl]; f.p.vy = col[SC_VY * POOL + sl]; f.p.vz = col[SC_VZ * POOL + sl];
           f.p.tcf = col[SC_TCF * POOL + sl]; f.p.nue = col[SC_NUE * POOL + sl]; f.p.t = col[SC_T * POOL + sl];
@@ -439,6 +441,7 @@ __global__ void __launch_bounds__(STREAM_THREADS, 2) k_advance_stream(const Mode
         }
         warp_max_into(&s_wmax[2 * warp + 1], seen, lane);
       }
+      if (!waited) cp_async_wait_all();
     }
     __syncthreads();
   }
