@@ -35,30 +35,26 @@ enum : int { SC_X = 0, SC_Y, SC_Z, SC_VX, SC_VY, SC_VZ, SC_TCF, SC_NUE, SC_T, SC
 // a warp can aggregate them with REDUX (resolution 1.5e-11 eV per event; the reference uses them only for the power balance)
 constexpr double TALLY_SCALE = 68719476736.0;
 
+// Shared-memory layout: every array sits at a COMPILE-TIME offset from the start; the only part whose size depends on the job (one tally
+// record per process) comes last.  Offsets that depend on P made ptxas 12.9 keep "base + 16 P" in a uniform register and then use that
+// register as the plain base for the per-thread sums in the ECR and AC+B instantiations (found with compute-sanitizer racecheck; the
+// thread-vs-stream test catches it as a wrong field gain) -- with constant offsets there is only one base to keep.
+struct Tally { unsigned long long gain, loss; unsigned int cnt, pad; };   // fixed point 2^-36 eV, see TALLY_SCALE
+constexpr size_t SM_COL = 0;                                                   // [SC_COLS][POOL] doubles
+constexpr size_t SM_HDR = SM_COL + static_cast<size_t>(SC_COLS) * POOL * 8;    // [R_HEADER] doubles: result header of the CTA
+constexpr size_t SM_GF = SM_HDR + static_cast<size_t>(R_HEADER) * 8;           // [STREAM_THREADS] doubles: per-thread field-gain sums
+constexpr size_t SM_TMAX = SM_GF + static_cast<size_t>(STREAM_THREADS) * 8;    // [2][STREAM_THREADS] doubles: per-thread energy maxima
+constexpr size_t SM_SCAN = SM_TMAX + static_cast<size_t>(STREAM_THREADS) * 16; // [16] u64: warp totals of the scan, range start, flight count
+constexpr size_t SM_USED = SM_SCAN + 16 * 8;                                   // [POOL] u32: draw counters
+constexpr size_t SM_LISTS = SM_USED + static_cast<size_t>(POOL) * 4;           // 4 x [POOL] u16
+constexpr size_t SM_FLAG = SM_LISTS + static_cast<size_t>(POOL) * 2 * 4;       // [POOL] u8
+constexpr size_t SM_MISC = SM_FLAG + POOL;                                     // [8] u32: rare-event counters
+constexpr size_t SM_RS = SM_MISC + 32;                                         // [16] i32: CTA-uniform round state
+constexpr size_t SM_TALLY = SM_RS + 64;                                        // [P] Tally
+static_assert(SM_TALLY % 8 == 0 && SM_SCAN % 8 == 0, "64-bit members need 8-byte offsets");
+
 __host__ __device__ inline size_t stream_smem_bytes(int P, int nEn_hist) {
-  size_t b = static_cast<size_t>(SC_COLS) * POOL * 8;       // state columns (+ time, id)
-  b += static_cast<size_t>(R_HEADER) * 8;                   // result header of the CTA
-  b += static_cast<size_t>(STREAM_THREADS) * 8;             // per-thread field-gain sums
-  b += static_cast<size_t>(STREAM_WARPS) * 16;              // per-warp energy maxima (end of interval, any event)
-  b += static_cast<size_t>(P) * 16;                         // gain, loss (fixed point)
-  b += 16 * 8;                                              // scan scratch (64-bit warp totals)
-  b += static_cast<size_t>(POOL) * 4;                       // draw counters
-  b += static_cast<size_t>(P) * 4;                          // counts
-  b += static_cast<size_t>(nEn_hist) * 4;                   // energy histogram
-  b += static_cast<size_t>(POOL) * 2 * 4;                   // four lists
-  b += POOL;                                                // flags
-  b += 32;                                                  // rare-event counters
-  b += 64;                                                  // CTA-uniform round state (cursors, list lengths)
-  return (b + 15) & ~static_cast<size_t>(15);
-}
-// rows of nu_tot staged in shared memory (all of them or none): the null test of every event reads two of them, and L1 is only what two
-// resident CTAs leave of the SM's 256 KB
-__host__ __device__ inline int stream_nu_rows(int P, int nE) {
-#ifdef LK_NO_NU_STAGE
-  return 0;
-#endif
-  const size_t base = stream_smem_bytes(P, 0), budget = (227u * 1024u) / 2u - 1024u;   // two CTAs per SM, 1 KB per CTA reserved by the driver
-  return (base + static_cast<size_t>(nE) * 8 <= budget) ? nE : 0;
+  return (SM_TALLY + static_cast<size_t>(P) * sizeof(Tally) + static_cast<size_t>(nEn_hist) * 4 + 15) & ~static_cast<size_t>(15);
 }
 
 struct StateId { State s; unsigned long long* id; };   // the 8 columns of s are one allocation: column c starts at s.x + c * n
@@ -73,7 +69,7 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 
 // warp-converged tally of one batch of collisions (BMC.C:1308-1328).  Lanes that chose the same process are found with MATCH,
 // their fixed-point energy changes are summed with REDUX in three 21-bit limbs, and one lane per process does the shared atomics.
-__device__ __forceinline__ void tally_collisions_fx(int chosen, double dE, unsigned int* s_cnt, unsigned long long* s_gain, unsigned long long* s_loss, int lane) {
+__device__ __forceinline__ void tally_collisions_fx(int chosen, double dE, Tally* s_tally, int lane) {
   const bool real = chosen >= 0;
   const unsigned rm = __ballot_sync(FULL, real);
   if (real) {
@@ -85,37 +81,32 @@ __device__ __forceinline__ void tally_collisions_fx(int chosen, double dE, unsig
     const unsigned l0 = __reduce_add_sync(peers, static_cast<unsigned>(l & 0x1FFFFFu)), l1 = __reduce_add_sync(peers, static_cast<unsigned>((l >> 21) & 0x1FFFFFu)),
                    l2 = __reduce_add_sync(peers, static_cast<unsigned>(l >> 42));
     if (lane == __ffs(peers) - 1) {
-      atomicAdd(&s_cnt[chosen], static_cast<unsigned int>(__popc(peers)));
+      Tally* t = s_tally + chosen;
+      atomicAdd(&t->cnt, static_cast<unsigned int>(__popc(peers)));
       const unsigned long long gs = static_cast<unsigned long long>(g0) + (static_cast<unsigned long long>(g1) << 21) + (static_cast<unsigned long long>(g2) << 42);
       const unsigned long long ls = static_cast<unsigned long long>(l0) + (static_cast<unsigned long long>(l1) << 21) + (static_cast<unsigned long long>(l2) << 42);
-      if (gs) atomicAdd(&s_gain[chosen], gs);
-      if (ls) atomicAdd(&s_loss[chosen], ls);
+      if (gs) atomicAdd(&t->gain, gs);
+      if (ls) atomicAdd(&t->loss, ls);
     }
   }
 }
 
-// null test against a nu_tot table that may live in shared memory (generic loads); BMC.C:1035-1053 like cold_null_test
+// branch-free null test (BMC.C:1035-1053, like cold_null_test)
 __device__ __forceinline__ bool stream_null_test(const Model& m, const double* __restrict__ nu_tab, double eps, double nue, double u, double& Rnu, bool& clamped, bool& exceeded) {
   Rnu = nue * u;
   int i1, i2; double w1, w2;
   cold_rows(m, eps, i1, i2, w1, w2);
   clamped = (i1 == m.nE - 1);
-  const double nu_here = w1 * nu_tab[i1] + w2 * nu_tab[i2];
+  const double nu_here = w1 * __ldg(&nu_tab[i1]) + w2 * __ldg(&nu_tab[i2]);
   exceeded = nu_here > nue;
   return !(Rnu > nu_here);                                         // BMC.C:1050
 }
 
 __device__ __forceinline__ int tid_now() { int t; asm volatile("mov.u32 %0, %%tid.x;" : "=r"(t)); return t; }   // re-read, never spilled
 
-// max of a non-negative double over the warp, folded into a shared slot by lane 0.  The bit pattern of a non-negative double orders like
-// an unsigned integer, so two REDUX (high word, then low word among the lanes that hold the high maximum) replace ten shuffles.
-__device__ __forceinline__ void warp_max_into(unsigned long long* slot, double v, int lane) {
-  const unsigned long long b = static_cast<unsigned long long>(__double_as_longlong(v));
-  const unsigned int hi = static_cast<unsigned int>(b >> 32), lo = static_cast<unsigned int>(b);
-  const unsigned int mh = __reduce_max_sync(FULL, hi);
-  const unsigned int ml = __reduce_max_sync(FULL, hi == mh ? lo : 0u);
-  if (lane == 0) { const unsigned long long mx = (static_cast<unsigned long long>(mh) << 32) | ml; if (mx > *slot) *slot = mx; }
-}
+// (Energy maxima are kept per THREAD in shared memory and reduced once at the end.  A warp-level REDUX.MAX folded into a shared slot was
+// cheaper on paper, but ptxas 12.9 allocated its uniform destination register on top of the live shared-memory base in two of the
+// fifteen instantiations of this kernel (ECR and AC+B, cold gas): tools/check_ur_clobber.py, tests/test_host_abi.py.)
 
 struct Flyer {   // one electron in the flight phase (two per lane)
   Particle p;
@@ -144,33 +135,28 @@ template <int FIELD, int GT, bool SAMPLE>
 __global__ void __launch_bounds__(STREAM_THREADS, 2) k_advance_stream(const Model m, const StateId sid, const Lists L, const Pending pend, const AdvArgs a,
                                                                        const HistGrid h, double* __restrict__ partials) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  double* col = reinterpret_cast<double*>(smem_raw);                                        // [SC_COLS][POOL]
-  double* s_hdr = col + SC_COLS * POOL;                                                     // [R_HEADER]
-  double* s_gf = s_hdr + R_HEADER;                                                          // [STREAM_THREADS] field gain, one slot per thread
-  unsigned long long* s_wmax = reinterpret_cast<unsigned long long*>(s_gf + STREAM_THREADS); // [STREAM_WARPS][2] bit patterns of non-negative doubles
-  unsigned long long* s_gain = s_wmax + 2 * STREAM_WARPS;
-  unsigned long long* s_loss = s_gain + m.P;
-  unsigned long long* s_scan = s_loss + m.P;                                                // [16]
-  unsigned int* s_used = reinterpret_cast<unsigned int*>(s_scan + 16);                      // [POOL]
-  unsigned int* s_cnt = s_used + POOL;                                                      // [P]
-  unsigned short* listF = reinterpret_cast<unsigned short*>(s_cnt + m.P);                   // [POOL] flights of this round
+  double* col = reinterpret_cast<double*>(smem_raw + SM_COL);                               // [SC_COLS][POOL]
+  double* s_hdr = reinterpret_cast<double*>(smem_raw + SM_HDR);                             // [R_HEADER]
+  double* s_gf = reinterpret_cast<double*>(smem_raw + SM_GF);                               // [STREAM_THREADS] field gain, one slot per thread
+  double* s_tmax = reinterpret_cast<double*>(smem_raw + SM_TMAX);                           // [2][STREAM_THREADS] max energy at t_sync / at any event
+  unsigned long long* s_scan = reinterpret_cast<unsigned long long*>(smem_raw + SM_SCAN);   // [16]
+  unsigned int* s_used = reinterpret_cast<unsigned int*>(smem_raw + SM_USED);               // [POOL]
+  unsigned short* listF = reinterpret_cast<unsigned short*>(smem_raw + SM_LISTS);           // [POOL] continuing flights of this round
   unsigned short* listR = listF + POOL;                                                     // [POOL] collisions of this round: cold first, thermal after
   unsigned short* listO = listR + POOL;                                                     // [POOL] slots retiring this round (output order; bit 15: attached)
   unsigned short* listE = listO + POOL;                                                     // [POOL] empty slots, in slot order
-  unsigned char* flag = reinterpret_cast<unsigned char*>(listE + POOL);                     // [POOL]
-  unsigned int* s_misc = reinterpret_cast<unsigned int*>(flag + POOL);                      // [MC_COUNT]
-  volatile int* s_rs = reinterpret_cast<volatile int*>(s_misc + 8);                         // [RS_COUNT] round state
-  const size_t fixed_bytes = stream_smem_bytes(m.P, 0);
-  double* s_nu = reinterpret_cast<double*>(smem_raw + fixed_bytes);                         // [a.pad] nu_tot rows, when they fit (a.pad = 0 otherwise)
+  unsigned char* flag = smem_raw + SM_FLAG;                                                 // [POOL]
+  unsigned int* s_misc = reinterpret_cast<unsigned int*>(smem_raw + SM_MISC);               // [MC_COUNT]
+  volatile int* s_rs = reinterpret_cast<volatile int*>(smem_raw + SM_RS);                   // [RS_COUNT] round state
+  Tally* s_tally = reinterpret_cast<Tally*>(smem_raw + SM_TALLY);                           // [P]
 
   {
   const int tid = tid_now();
-  for (int k = tid; k < m.P; k += STREAM_THREADS) { s_gain[k] = 0; s_loss[k] = 0; s_cnt[k] = 0; }
+  for (int k = tid; k < m.P; k += STREAM_THREADS) { s_tally[k].gain = 0; s_tally[k].loss = 0; s_tally[k].cnt = 0; }
   if (tid < R_HEADER) s_hdr[tid] = 0;
   s_gf[tid] = 0;
-  if (tid < 2 * STREAM_WARPS) s_wmax[tid] = 0ull;
+  s_tmax[tid] = 0; s_tmax[STREAM_THREADS + tid] = 0;
   if (tid < MC_COUNT) s_misc[tid] = 0;
-  for (int j = tid; j < static_cast<int>(a.pad); j += STREAM_THREADS) s_nu[j] = __ldg(&m.nu_tot[j]);
   reinterpret_cast<unsigned int*>(flag)[tid] = 0u;   // all slots FL_EMPTY
 
   // the CTA's range [lo, lo + len) of the ensemble; cursors are CTA-uniform offsets into it.  Column c of the state is sid.s.x + lo + c * a.n.
@@ -277,7 +263,7 @@ __global__ void __launch_bounds__(STREAM_THREADS, 2) k_advance_stream(const Mode
             col[SC_T * POOL + sl] = a.t0; s_used[sl] = 0;
           }
         }
-        warp_max_into(&s_wmax[2 * warp], eps_end, lane);
+        s_tmax[tid] = fmax(s_tmax[tid], eps_end);
       }
     }
     cp_async_commit();
@@ -335,8 +321,8 @@ __global__ void __launch_bounds__(STREAM_THREADS, 2) k_advance_stream(const Mode
           s_used[sl] = rng.used;
           flag[sl] = outcome;
         }
-        tally_collisions_fx(chosen, dE, s_cnt, s_gain, s_loss, lane);
-        warp_max_into(&s_wmax[2 * warp + 1], seen, lane);
+        tally_collisions_fx(chosen, dE, s_tally, lane);
+        s_tmax[STREAM_THREADS + tid] = fmax(s_tmax[STREAM_THREADS + tid], seen);
       }
     }
     __syncwarp();   // the warp's own collision results are visible to all its lanes
@@ -352,11 +338,11 @@ __global__ void __launch_bounds__(STREAM_THREADS, 2) k_advance_stream(const Mode
       const int nFlr = s_rs[RS_NFL], nB = s_rs[RS_NBC] + s_rs[RS_NBT], nRetr = s_rs[RS_NRET], nRefr = s_rs[RS_NREFILL];
       const int kc = (nB + 31) >> 5, cc = (nFlr + 31) >> 5, rc = (nRefr + 31) >> 5;                // 32-wide chunks: collided, continuing, refilled
       const int nK = (kc - warp + STREAM_WARPS - 1) >> 3;                                          // this warp's collided chunks (warp, warp + 8, ...)
-      const int wrot = (warp + kc) & (STREAM_WARPS - 1);                                           // continuing chunk c -> warp (c - kc) mod 8: evens out the totals
+      const int wrot = (warp - kc - rc) & (STREAM_WARPS - 1);                                      // continuing chunk c -> warp (c + kc + rc) mod 8: the round-robin goes on where the owner-bound chunks ended
       const int nC = (cc - wrot + STREAM_WARPS - 1) >> 3;
       const int nR = (rc - warp + STREAM_WARPS - 1) >> 3;                                          // refill ranks [32 g, 32 g + 32), g = warp, warp + 8, ...: issued by these very threads
       const int nA = nK + nC, nItems = nA + nR;
-      const double* __restrict__ nu_tab = a.pad ? s_nu : m.nu_tot;
+      const double* __restrict__ nu_tab = m.nu_tot;
       const double rnu = recip_for_div(a.nu_trial);
       bool waited = false;
 #pragma unroll 1
@@ -439,7 +425,7 @@ __global__ void __launch_bounds__(STREAM_THREADS, 2) k_advance_stream(const Mode
 #pragma unroll
           for (int j = 0; j < 2; ++j) { if (e[j].clamped) atomicAdd(&s_misc[MC_CLAMP], 1u); if (e[j].exceeded) atomicAdd(&s_misc[MC_NUEX], 1u); }
         }
-        warp_max_into(&s_wmax[2 * warp + 1], seen, lane);
+        s_tmax[STREAM_THREADS + tid] = fmax(s_tmax[STREAM_THREADS + tid], seen);
       }
       if (!waited) cp_async_wait_all();
     }
@@ -449,7 +435,7 @@ __global__ void __launch_bounds__(STREAM_THREADS, 2) k_advance_stream(const Mode
   const int tid = tid_now();
   if (tid == 0) {   // header of the CTA: real collisions = sum of the per-process counts; rare-event counters; fixed-order sums
     double nr = 0;
-    for (int k = 0; k < m.P; ++k) nr += static_cast<double>(s_cnt[k]);
+    for (int k = 0; k < m.P; ++k) nr += static_cast<double>(s_tally[k].cnt);
     s_hdr[R_N_REAL] = nr;
     // events = non-partial flights = (flights flown) - (electrons of the range); null = events - real  (BMC.C:1308-1320)
     const unsigned long long flights = *reinterpret_cast<volatile unsigned long long*>(&s_scan[9]) - s_misc[MC_ATT];
@@ -460,9 +446,8 @@ __global__ void __launch_bounds__(STREAM_THREADS, 2) k_advance_stream(const Mode
     double gf = 0, m0 = 0, m1 = 0;
     for (int w = 0; w < STREAM_WARPS; ++w) {   // same order as a warp-shuffle tree over lanes followed by a sum over warps would not be needed: any fixed order is reproducible
       double ws = 0;
-      for (int l = 0; l < 32; ++l) ws += s_gf[w * 32 + l];
+      for (int l = 0; l < 32; ++l) { ws += s_gf[w * 32 + l]; m0 = fmax(m0, s_tmax[w * 32 + l]); m1 = fmax(m1, s_tmax[STREAM_THREADS + w * 32 + l]); }
       gf += ws;
-      m0 = fmax(m0, __longlong_as_double(static_cast<long long>(s_wmax[2 * w]))); m1 = fmax(m1, __longlong_as_double(static_cast<long long>(s_wmax[2 * w + 1])));
     }
     s_hdr[R_GAIN_FIELD] = gf; s_hdr[R_MAX_EPS] = m0; s_hdr[R_MAX_EPS_SEEN] = fmax(m0, m1);
   }
@@ -472,9 +457,9 @@ __global__ void __launch_bounds__(STREAM_THREADS, 2) k_advance_stream(const Mode
     double* out = partials + static_cast<size_t>(blockIdx.x) * plen;
     for (int j = tid; j < R_HEADER; j += STREAM_THREADS) out[j] = s_hdr[j];
     for (int k = tid; k < m.P; k += STREAM_THREADS) {
-      out[R_HEADER + k] = static_cast<double>(s_cnt[k]);
-      out[R_HEADER + m.P + k] = static_cast<double>(s_gain[k]) / TALLY_SCALE;
-      out[R_HEADER + 2 * m.P + k] = -static_cast<double>(s_loss[k]) / TALLY_SCALE;
+      out[R_HEADER + k] = static_cast<double>(s_tally[k].cnt);
+      out[R_HEADER + m.P + k] = static_cast<double>(s_tally[k].gain) / TALLY_SCALE;
+      out[R_HEADER + 2 * m.P + k] = -static_cast<double>(s_tally[k].loss) / TALLY_SCALE;
     }
   }
 }

@@ -193,13 +193,11 @@ int launch_advance(lokib200_engine* h, bool sample, const Model& m, const AdvArg
 
 template <int F, int G>
 int launch_stream_t(lokib200_engine* h, const Model& m, const AdvArgs& a, const HistGrid& hg) {
-  const int nu_rows = stream_nu_rows(h->P, h->nE);   // nu_tot staged in shared memory when it fits beside the pool
-  const size_t smem = stream_smem_bytes(h->P, 0) + static_cast<size_t>(nu_rows) * 8;
+  const size_t smem = stream_smem_bytes(h->P, 0);
   CK(cudaFuncSetAttribute(k_advance_stream<F, G, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   CK(cudaFuncSetAttribute(k_advance_stream<F, G, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   const StateId sid{h->st, h->d_id};   // the kernel addresses column c as st.x + c * n (one allocation, lokib200_create)
-  AdvArgs as = a; as.pad = static_cast<unsigned int>(nu_rows);
-  k_advance_stream<F, G, false><<<h->tile_blocks, STREAM_THREADS, smem, h->stream>>>(m, sid, h->lists, h->pend, as, hg, h->d_adv_part);
+  k_advance_stream<F, G, false><<<h->tile_blocks, STREAM_THREADS, smem, h->stream>>>(m, sid, h->lists, h->pend, a, hg, h->d_adv_part);
   return 0;
 }
 template <int F>

@@ -41,3 +41,17 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "lokioracle" not in src and "oracle/" not in src, f
+
+
+def test_no_reduction_result_on_a_live_uniform_register():
+    """ptxas 12.9 once placed the uniform destination of a REDUX on top of the live shared-memory base in two instantiations of the
+    advance kernel (wild LDS address, found with compute-sanitizer).  The SASS of the built library is scanned for that pattern."""
+    import shutil
+    import sys
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not on PATH")
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import check_ur_clobber
+    import loki_mc_b200 as lk
+    assert check_ur_clobber.scan(lk.lib_path()) == []
+    assert check_ur_clobber.scan_derived_bases(lk.lib_path()) == []
