@@ -303,6 +303,7 @@ def main():
     ms_dev = e0.elapsed_time(e1)
     clocks = sampler.stop()
     adv_ms, adv_n = eng.kernel_time_ms()
+    fp64_peak = eng.measure_fp64_peak() if rank == 0 else None
     launches = eng.launch_count() - launches0
     ev_dev = float(d_events.item())   # already the sum over ranks when world > 1
 
@@ -313,11 +314,14 @@ def main():
     final = d_res.cpu().numpy()
     if rank == 0:
         peak, peak_src = measured_hbm_peak()
-        traffic = None
-        try:   # DRAM bytes of one K1 launch from the committed ncu --set full capture (same workload only)
+        traffic, fp64 = None, None
+        try:   # DRAM bytes and FP64 operations of one K1 launch from the committed ncu captures (same workload only)
             tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
             if tj["electrons"] == n and args.model == "n2_aniso":
                 traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
+                # second ceiling of SURVEY.md 8(d): FP64 pipe.  flop per event from ncu's SASS counters (DFMA = 2), peak = DFMA chain measured live
+                flop_per_event = tj["fp64_flop"] / tj["events"]
+                fp64 = dict(flop_per_event=flop_per_event, peak=fp64_peak, unit="TFLOP/s", peak_source="measured live (lokib200_measure_fp64_peak: 16 DFMA chains per thread)")
         except Exception:
             pass
         ev_per_launch_rank = ev_dev / world / args.steps
@@ -335,6 +339,10 @@ def main():
             roofline=dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=(achieved / peak) if achieved else None, traffic=traffic,
                           kernel="k_advance", kernel_ms=adv_ms, kernel_launches=adv_n, bytes_per_event=STATE_BYTES_PER_EVENT, peak_source=peak_src,
                           kernel_share_of_step=adv_ms * adv_n / ms_dev if ms_dev > 0 else None))
+        if fp64 is not None and adv_ms > 0:
+            fp64["achieved"] = fp64["flop_per_event"] * ev_per_launch_rank / (adv_ms * 1e-3) / 1e12
+            fp64["frac"] = fp64["achieved"] / fp64["peak"]
+            line["roofline"]["fp64"] = fp64
         if world == 1 and not args.no_cpu_baseline:
             try:
                 line["cpu_baseline"] = cpu_baseline_port(args.model, mean_e)

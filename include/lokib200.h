@@ -200,6 +200,9 @@ int lokib200_check_nu_trial(lokib200_engine* h, double max_energy, double horizo
 int64_t lokib200_launch_count(const lokib200_engine* h);
 /* average device time [ms] of the advance kernel over the launches since the last call (CUDA events on the engine's stream) */
 int lokib200_kernel_time_ms(lokib200_engine* h, double* advance_ms, int64_t* launches);
+/* measurement aid ("the builder must measure the DFMA peak on the box"): runs a register-resident chain of
+ * independent DFMAs on every SM of the engine's device and returns the sustained rate in TFLOP/s (one DFMA = 2 flop) */
+int lokib200_measure_fp64_peak(lokib200_engine* h, double* tflops);
 
 
 /* ------------------------------------------------------------------------------------------------------------------------

@@ -142,7 +142,7 @@ SYMBOLS = ["lokib200_abi_version", "lokib200_device_count", "lokib200_create", "
            "lokib200_nu_max_at", "lokib200_init_ensemble", "lokib200_set_ensemble", "lokib200_get_ensemble", "lokib200_time",
            "lokib200_advance_to_sync", "lokib200_advance_to_sync_device", "lokib200_set_histogram_grid", "lokib200_sample_histograms",
            "lokib200_fetch_histograms", "lokib200_step_injected", "lokib200_max_accel_energy", "lokib200_check_nu_trial",
-           "lokib200_launch_count", "lokib200_kernel_time_ms", "lokib200_get_config", "lokib200_process_count", "lokib200_get_rel_densities",
+           "lokib200_launch_count", "lokib200_kernel_time_ms", "lokib200_measure_fp64_peak", "lokib200_get_config", "lokib200_process_count", "lokib200_get_rel_densities",
            "lokib200_sample_moments", "lokib200_regrid_energy_histograms", "lokib200_read_result", "lokib200_job_create", "lokib200_job_solve", "lokib200_job_results",
            "lokib200_job_process_outputs", "lokib200_job_time_series", "lokib200_job_histograms", "lokib200_job_periodic",
            "lokib200_job_periodic_diffusion", "lokib200_job_conditions", "lokib200_job_evdf_max_speed", "lokib200_job_last_error", "lokib200_job_destroy"]
@@ -190,6 +190,7 @@ def lib():
     L.lokib200_check_nu_trial.argtypes = [vp, C.c_double, C.c_double, C.c_double, c_dp]
     L.lokib200_launch_count.argtypes = [vp]; L.lokib200_launch_count.restype = C.c_int64
     L.lokib200_kernel_time_ms.argtypes = [vp, c_dp, c_lp]
+    L.lokib200_measure_fp64_peak.argtypes = [vp, c_dp]
     L.lokib200_sample_moments.argtypes = [vp, c_dp]
     L.lokib200_regrid_energy_histograms.argtypes = [vp, C.c_double]
     L.lokib200_read_result.argtypes = [vp, c_dp]
@@ -403,6 +404,11 @@ class Engine:
         ms = C.c_double(); n = C.c_int64()
         self._check(self.L.lokib200_kernel_time_ms(self.h, C.byref(ms), C.byref(n)))
         return ms.value, n.value
+
+    def measure_fp64_peak(self):
+        v = C.c_double()
+        self._check(self.L.lokib200_measure_fp64_peak(self.h, C.byref(v)))
+        return v.value
 
 
 class Job:

@@ -295,6 +295,22 @@ __global__ void __launch_bounds__(ADV_THREADS, 2) k_advance(const Model m, const
   if (SAMPLE && h.enabled) flush_energy_histogram(h, s_eeh);
 }
 
+// FP64 roofline denominator: 16 independent DFMA chains per thread, nothing but the FP64 pipe (bench.py: roofline.fp64)
+__global__ void __launch_bounds__(256) k_dfma_peak(double* out, int iters, double seed) {
+  double acc[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) acc[j] = seed + j * 1e-9 + threadIdx.x * 1e-12;
+  const double m = seed, c = 1e-9;
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) acc[j] = __fma_rn(acc[j], m, c);
+  }
+  double t = 0;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) t += acc[j];
+  if (t == 123.456) out[blockIdx.x] = t;   // never true: keeps the chains alive
+}
+
 // ------------------------------------------------------------------ K3 ------------------------------------------------------------------
 // ensemble sums + histograms as a separate pass (used when births/deaths can change the ensemble at t_sync)
 __global__ void __launch_bounds__(ADV_THREADS) k_sample(const State s, long long n, const HistGrid h, int P, double* __restrict__ partials) {

@@ -14,11 +14,7 @@
 #include <string>
 #include <vector>
 
-#ifdef LK_STREAM_PREV
-#include "lk_stream_prev.cuh"
-#else
 #include "lk_stream.cuh"
-#endif
 
 using namespace lk;
 
@@ -856,6 +852,28 @@ int lokib200_kernel_time_ms(lokib200_engine* h, double* advance_ms, int64_t* lau
   if (advance_ms) *advance_ms = h->ev_used ? total / static_cast<double>(h->ev_used) : 0.0;
   if (launches) *launches = static_cast<int64_t>(h->ev_used);
   h->ev_used = 0;
+  return 0;
+}
+
+int lokib200_measure_fp64_peak(lokib200_engine* h, double* tflops) {
+  if (!h || !tflops) return LOKIB200_ERR_INVALID;
+  CK(cudaSetDevice(h->cfg.device));
+  const int blocks = h->sm_count * 8, threads = 256, iters = 4096;
+  double* d_out = nullptr;
+  CK(cudaMalloc(&d_out, sizeof(double) * blocks));
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  float best = 1e30f;
+  for (int rep = 0; rep < 5; ++rep) {
+    CK(cudaEventRecord(e0, h->stream));
+    k_dfma_peak<<<blocks, threads, 0, h->stream>>>(d_out, iters, 1.0000001);
+    CK(cudaEventRecord(e1, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    float ms = 0; CK(cudaEventElapsedTime(&ms, e0, e1));
+    if (rep > 0 && ms < best) best = ms;
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d_out);
+  *tflops = 2.0 * 16.0 * static_cast<double>(iters) * threads * blocks / (best * 1e-3) / 1e12;
   return 0;
 }
 
