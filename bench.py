@@ -4,6 +4,7 @@ Monte Carlo hot path.
 
   python bench.py --gpus N --steps K --warmup W            our arm (one process per GPU; torchrun for N > 1)
   python bench.py --impl reference --gpus N --steps K ...  the reference's own CPU implementation on the host cores
+  python bench.py --time-to-3sigma                         second metric: one setup file end to end, checked against the reference's replicas
 
 Workload (BASELINE.json configs[1]): N2, DC field, E/N = 100 Td point of the sweep, anisotropic scattering (Born-dipole
 rotational, Surendra excitation, momentum-conserving ionization), 1e7 electrons per GPU, reference cadence: one synchronisation
@@ -176,6 +177,56 @@ def run_reference_arm(args):
     print(json.dumps(line))
 
 
+def run_time_to_3sigma(args):
+    """BASELINE.json's second metric: wall time from job start until the run's own stop criterion is met with every swarm parameter within
+    3 sigma_eff of the reference.  Setup: tests/fixtures/Input/fx/setup_out_dc.in (two gases, anisotropic models, two E/N
+    jobs) at 2e4 electrons, through the setup-file entry point (lokib200_run_setup: parse -> solve -> post-process -> write the output
+    folder).  sigma_eff per parameter = max(reference's reported std, scatter of its 10 replicas, this run's reported std), from
+    tests/golden/ensemble_fixture.json.  Beside it: the unmodified reference on the same setup on the host cores, when oracle/_ref is there."""
+    import shutil
+    import tempfile
+    import loki_mc_b200 as lk
+    from oracle import run_reference as rr
+    fix = os.path.join(ROOT, "tests", "fixtures", "Input")
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "ensemble_fixture.json")))["jobs"]
+    n = 20000
+    text = open(os.path.join(fix, "fx", "setup_out_dc.in")).read().replace("nElectrons: 400", "nElectrons: %d" % n)
+    tmp = tempfile.mkdtemp()
+    path = os.path.join(tmp, "job.in")
+    with open(path, "w") as f:
+        f.write(text)
+    lk.run_setup(fix, path, os.path.join(tmp, "warm"), verbose=False)          # untimed: context creation, module load
+    t0 = time.perf_counter()
+    lk.run_setup(fix, path, os.path.join(tmp, "out"), verbose=False)
+    wall = time.perf_counter() - t0
+    worst, checked, events = 0.0, 0, 0.0
+    for sub in sorted(os.listdir(os.path.join(tmp, "out", "fx_dc"))):
+        d = os.path.join(tmp, "out", "fx_dc", sub)
+        if not os.path.isdir(d):
+            continue
+        mine, g = rr.parse_swarm(os.path.join(d, "swarmParameters.txt")), gold["setup_out_dc/" + sub]
+        det = rr.parse_details(os.path.join(d, "MCSimDetails.txt"))
+        events += det["total number of real collisions"] + det["total number of null collisions"]
+        for key, mean in g["mean"].items():
+            if key.endswith("v_x") or mean == 0 or key not in mine:
+                continue                                                         # components that vanish by symmetry are pure noise
+            rel = max(g["reported_relstd"].get(key, 0.0), g["std"][key] / abs(mean), mine.get(key + "/relstd", 0.0), 4e-3)
+            worst = max(worst, abs(mine[key] - mean) / (rel * abs(mean)))
+            checked += 1
+    line = dict(metric="time_to_3sigma_s", value=wall, unit="s", higher_is_better=False, n_gpus=1, data="synthetic fixture gases (tests/fixtures/Input/fx)",
+                config=dict(workload="fx/setup_out_dc.in: 2 jobs (E/N = 20, 80 Td), 2e4 electrons, reference stop criterion", electrons=n),
+                within_3sigma=bool(worst <= 3.0), worst_deviation_sigma=worst, parameters_checked=checked, events=events, events_per_s=events / wall)
+    if rr.available():
+        dst = os.path.join(rr.REFDIR, "Input", "fx")
+        shutil.rmtree(dst, ignore_errors=True)
+        shutil.copytree(os.path.join(fix, "fx"), dst)
+        res = rr.run(text, "fx_dc")
+        line["reference"] = dict(value=res["wall"], unit="s", cores=res["threads"], kind="reference",
+                                 sample="unmodified lokimc (oracle/_ref) on the same setup file and electron count, all host threads")
+    shutil.rmtree(tmp, ignore_errors=True)
+    print(json.dumps(line))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -189,7 +240,10 @@ def main():
     ap.add_argument("--ref-points", type=int, default=500)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--batch", type=int, default=16, help="device leg: intervals whose result vectors share one collective")
+    ap.add_argument("--time-to-3sigma", action="store_true", help="second metric of BASELINE.json: setup file in, swarm parameters out, on one GPU")
     args = ap.parse_args()
+    if args.time_to_3sigma:
+        return run_time_to_3sigma(args)
     if args.warmup < 3:
         args.warmup = 3
     if args.impl == "reference":

@@ -1,24 +1,27 @@
 // lk_stream.cuh -- K1, streaming-pool form: the production advance kernel for large ensembles.
 //
 // (Design history, all measured on B200 and kept under profiles/: one electron per thread -> 6 of 32 lanes active, I-cache thrash;
-//  CTA tile drained to empty -> 8 of 12 warps waiting at barriers; this CTA-wide pool with refill; warp-private pools -> I-cache thrash.)
+//  CTA tile drained to empty -> 8 of 12 warps waiting at barriers; CTA-wide pool with refill, two barrier intervals per round;
+//  warp-private pools -> I-cache thrash; this form.  DESIGN.md section 5 has the numbers.)
 //
 // A CTA owns a contiguous range of the ensemble and keeps a POOL of electrons resident in shared memory.  Every round
-//   (1) one block scan over the slot flags RETIRES the electrons that reached t_sync (written back in arrival order, so stores are
-//       dense), REFILLS the freed slots from the CTA's input cursor (dense loads) and builds the two work lists in slot order;
-//   (2) phase B runs the collisions of the electrons that passed the null test      (BMC.C:916-1031, 1054-1280);
-//   (3) phase A runs one free flight + null-collision test for every active electron (BMC.C:650-667, 804-905, 1035-1053).
-// Both phases run on compacted lists, so warps are full, and all warps of the CTA execute the same code at the same time, which is
-// what keeps the instruction cache effective (a variant with warp-private pools and no CTA barriers was measured 1.7x slower:
-// 16 desynchronised warps thrash the I-cache, stall_no_instruction 7.0 per issue).  The pool stays full until the CTA's range is
-// exhausted, so the Poisson tail is paid once per CTA, not once per tile.  Collisions wait in the pool until a whole CTA-iteration
-// of them (256) is available.
+//   (1) one block scan over the slot flags builds four lists in slot order: continuing flights, collisions (cold-gas picks first,
+//       thermal-target picks after), retiring slots, empty slots;                                                     [barrier]
+//   (2) retire + refill by rank: thread t owns ranks t, t + 256, ...; it writes the r-th retiring slot to output element out + r
+//       (dense stores) and loads input element in + r into the same slot with cp.async (dense loads);
+//   (3) collisions of the electrons that passed the null test, in chunks of 32, chunk c on warp c % 8       (BMC.C:916-1031, 1054-1280);
+//   (4) one free flight + null-collision test per electron, two electrons per lane                (BMC.C:650-667, 804-905, 1035-1053):
+//       a warp flies the chunks it collided in (3), its share of the continuing chunks and - once its own copies have landed - the
+//       electrons its threads refilled in (2).  Nothing a warp reads was written by another warp in this round.       [barrier]
+// All warps of the CTA execute the same phase at about the same time, which is what keeps the instruction cache effective (a variant
+// with warp-private pools and no CTA barriers was measured 1.7x slower: 16 desynchronised warps thrash the I-cache).  The pool stays
+// full until the CTA's range is exhausted, so the Poisson tail is paid once per CTA, not once per tile.  Collisions wait in the pool
+// until a whole CTA-iteration of them (256) is available.
 // Electrons therefore PERMUTE inside the CTA's range (in place: the write cursor never overtakes the read cursor); the `id`
 // column travels with each electron and keys its counter-based draw stream, so the physics is bit-identical to the
 // one-thread-per-electron kernel.  The schedule involves no atomics, hence it is deterministic.
 #pragma once
 #include "lk_tile.cuh"
-// (this file is the v10 form of the kernel: see the round structure below)
 
 namespace lk {
 
@@ -123,14 +126,6 @@ enum : int { MC_BORN = 0, MC_ATT, MC_CLAMP, MC_NUEX, MC_COUNT };   // rare event
 // live across the inlined collision code is a spill candidate, and local-memory spills miss the small L1 (profiles/r1_v10_*)
 enum : int { RS_IN = 0, RS_OUT, RS_LEN, RS_NFL, RS_NBC, RS_NBT, RS_NRET, RS_NREFILL, RS_COUNT };   // (the 64-bit ones, range start and flight count, sit in s_scan[8], s_scan[9])
 
-// Round structure (one CTA, 256 threads, POOL resident electrons):
-//   (1) block scan over the slot flags -> lists: F = [continuing | collided this round | refilled this round], R = [cold | thermal], O/K/I retire + refill
-//   (2) retire (dense stores) + refill (cp.async, lands during (3) and (4a))
-//   (3) collisions of list R                       -- no barrier after it: a warp that is done goes on with (4a)
-//   (4a) flights of the continuing electrons        -- touch neither the slots of (3) nor the refilled ones
-//        cp.async wait + barrier
-//   (4b) flights of the collided and refilled electrons; refilled electrons arrive with a free time, so their warps skip the draw's logarithm
-//   barrier
 template <int FIELD, int GT, bool SAMPLE>
 __global__ void __launch_bounds__(STREAM_THREADS, 2) k_advance_stream(const Model m, const StateId sid, const Lists L, const Pending pend, const AdvArgs a,
                                                                        const HistGrid h, double* __restrict__ partials) {
