@@ -392,7 +392,7 @@ def main():
             gpu_launches=int(launches * world), clocks=clocks,
             roofline=dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=(achieved / peak) if achieved else None, traffic=traffic,
                           kernel="k_advance", kernel_ms=adv_ms, kernel_launches=adv_n, bytes_per_event=STATE_BYTES_PER_EVENT, peak_source=peak_src,
-                          kernel_share_of_step=adv_ms * adv_n / ms_dev if ms_dev > 0 else None))
+                          kernel_share_of_step=adv_ms * args.steps / ms_dev if ms_dev > 0 else None))   # (the engine times at most its first 256 launches per leg)
         if fp64 is not None and adv_ms > 0:
             fp64["achieved"] = fp64["flop_per_event"] * ev_per_launch_rank / (adv_ms * 1e-3) / 1e12
             fp64["frac"] = fp64["achieved"] / fp64["peak"]

@@ -77,9 +77,13 @@ struct lokib200_engine {
   double max_eedf_energy = 0;
 
   // kernel timing
+  // kernel timing: event pairs around the advance kernel of the first EV_CAP intervals after each lokib200_kernel_time_ms call (a job of 1e5
+  // intervals must neither create 2e5 events nor pay two cudaEventRecord per interval)
+  static constexpr size_t EV_CAP = 256;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pool;
   size_t ev_used = 0;
   bool timing = true;
+  size_t stream_smem_set = 0;   // dynamic shared memory the streaming kernel's attributes were last set for (0 = never)
 };
 
 namespace {
@@ -190,8 +194,11 @@ int launch_advance(lokib200_engine* h, bool sample, const Model& m, const AdvArg
 template <int F, int G>
 int launch_stream_t(lokib200_engine* h, const Model& m, const AdvArgs& a, const HistGrid& hg) {
   const size_t smem = stream_smem_bytes(h->P, 0);
-  CK(cudaFuncSetAttribute(k_advance_stream<F, G, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-  CK(cudaFuncSetAttribute(k_advance_stream<F, G, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  if (h->stream_smem_set != smem) {   // (an engine uses one instantiation on one device)
+    CK(cudaFuncSetAttribute(k_advance_stream<F, G, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    CK(cudaFuncSetAttribute(k_advance_stream<F, G, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    h->stream_smem_set = smem;
+  }
   const StateId sid{h->st, h->d_id};   // the kernel addresses column c as st.x + c * n (one allocation, lokib200_create)
   k_advance_stream<F, G, false><<<h->tile_blocks, STREAM_THREADS, smem, h->stream>>>(m, sid, h->lists, h->pend, a, hg, h->d_adv_part);
   return 0;
@@ -619,7 +626,8 @@ int lokib200_advance_to_sync_device(lokib200_engine* h, double nu_trial, double 
   const bool fused = sample && !h->has_pc;
   HistGrid no_hist{};   // histograms are sampled by lokib200_sample_histograms
   cudaEvent_t e0 = nullptr, e1 = nullptr;
-  if (h->timing) {
+  const bool timed = h->timing && h->ev_used < lokib200_engine::EV_CAP;
+  if (timed) {
     if (h->ev_used == h->ev_pool.size()) {
       cudaEvent_t a0, a1; CK(cudaEventCreate(&a0)); CK(cudaEventCreate(&a1));
       h->ev_pool.emplace_back(a0, a1);
@@ -629,7 +637,7 @@ int lokib200_advance_to_sync_device(lokib200_engine* h, double nu_trial, double 
   }
   if (h->use_tile) { if ((rc = launch_stream(h, m, a, no_hist))) return rc; h->last_adv_blocks = h->tile_blocks; h->permuted = true; }
   else { if ((rc = launch_advance(h, fused, m, a, no_hist))) return rc; h->last_adv_blocks = h->adv_blocks; }
-  if (h->timing) CK(cudaEventRecord(e1, h->stream));
+  if (timed) CK(cudaEventRecord(e1, h->stream));
   ++h->launches;
   CK(cudaGetLastError());
   const double* smp = nullptr;
