@@ -198,22 +198,25 @@ __global__ void __launch_bounds__(STREAM_THREADS, 2) k_advance_stream(const Mode
     int eFl = static_cast<int>(excl & 0xFFFu), eRc = static_cast<int>((excl >> 12) & 0xFFFu), eRt = static_cast<int>((excl >> 24) & 0xFFFu),
         eRet = static_cast<int>((excl >> 36) & 0xFFFu), eEmp = static_cast<int>((excl >> 48) & 0xFFFu);
     unsigned int new_f4 = f4;
+    // branch-free: the four lists are contiguous ([F | R | O | E], POOL entries each), so every slot computes ONE destination index
+    // (POOL * 4 = nowhere) and does one predicated store; the five kinds would otherwise be five divergent paths per slot
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       const int sl = tid * 4 + q;
-      unsigned int f = (f4 >> (8 * q)) & 0xFFu;
-      if (f == FL_DONE || f == FL_DEAD) {
-        listO[eRet] = static_cast<unsigned short>(sl | (f == FL_DEAD ? 0x8000 : 0));
-        f = (eRet < nRefill) ? FL_FLIGHT : FL_EMPTY;               // refilled by the thread that writes it back, flown by that thread
-        ++eRet;
-      } else if (f == FL_EMPTY) {
-        listE[eEmp] = static_cast<unsigned short>(sl);
-        if (nRet + eEmp < nRefill) f = FL_FLIGHT;
-        ++eEmp;
-      } else if (f == FL_FLIGHT) { listF[eFl] = static_cast<unsigned short>(sl); ++eFl; }
-      else if (f == FL_REAL) { if (eRc < nBc) listR[eRc] = static_cast<unsigned short>(sl); ++eRc; }
-      else if (f == FL_REALT) { if (eRt < nBt) listR[nBc + eRt] = static_cast<unsigned short>(sl); ++eRt; }
-      new_f4 = (new_f4 & ~(0xFFu << (8 * q))) | (f << (8 * q));
+      const unsigned int f = (f4 >> (8 * q)) & 0xFFu;
+      const bool isRet = (f == FL_DONE || f == FL_DEAD), isEmp = (f == FL_EMPTY), isFl = (f == FL_FLIGHT), isRc = (f == FL_REAL), isRt = (f == FL_REALT);
+      const bool refilled = isRet ? (eRet < nRefill) : (isEmp && nRet + eEmp < nRefill);
+      int dst = 4 * POOL;
+      dst = isFl ? eFl : dst;
+      dst = (isRc && eRc < nBc) ? POOL + eRc : dst;
+      dst = (isRt && eRt < nBt) ? POOL + nBc + eRt : dst;
+      dst = isRet ? 2 * POOL + eRet : dst;
+      dst = isEmp ? 3 * POOL + eEmp : dst;
+      const unsigned int val = static_cast<unsigned int>(sl) | ((f == FL_DEAD) ? 0x8000u : 0u);
+      if (dst < 4 * POOL) listF[dst] = static_cast<unsigned short>(val);
+      eFl += isFl; eRc += isRc; eRt += isRt; eRet += isRet; eEmp += isEmp;
+      const unsigned int nf = (isRet || isEmp) ? (refilled ? static_cast<unsigned int>(FL_FLIGHT) : static_cast<unsigned int>(FL_EMPTY)) : f;
+      new_f4 = (new_f4 & ~(0xFFu << (8 * q))) | (nf << (8 * q));
     }
     reinterpret_cast<unsigned int*>(flag)[tid] = new_f4;
     const int nF = nFl + nRefill + nBc + nBt;
