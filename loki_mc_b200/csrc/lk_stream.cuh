@@ -53,11 +53,19 @@ constexpr size_t SM_LISTS = SM_USED + static_cast<size_t>(POOL) * 4;           /
 constexpr size_t SM_FLAG = SM_LISTS + static_cast<size_t>(POOL) * 2 * 4;       // [POOL] u8
 constexpr size_t SM_MISC = SM_FLAG + POOL;                                     // [8] u32: rare-event counters
 constexpr size_t SM_RS = SM_MISC + 32;                                         // [16] i32: CTA-uniform round state
-constexpr size_t SM_TALLY = SM_RS + 64;                                        // [P] Tally
-static_assert(SM_TALLY % 8 == 0 && SM_SCAN % 8 == 0, "64-bit members need 8-byte offsets");
+// The first NU_STAGE_ROWS rows of nu_tot (the null test of every event interpolates two of them; they are the rows nearly every electron
+// is in) are staged here when the tally records still fit behind them; otherwise the tally starts at SM_NU and the kernel reads nu_tot from
+// global memory only.  Both starts are compile-time constants.
+constexpr int NU_STAGE_ROWS = 1024;
+constexpr size_t SM_NU = SM_RS + 64;                                           // [NU_STAGE_ROWS] doubles, optional
+constexpr size_t SM_TALLY_STAGED = SM_NU + static_cast<size_t>(NU_STAGE_ROWS) * 8;   // [P] Tally when the rows are staged
+constexpr size_t SM_TALLY_PLAIN = SM_NU;                                       // [P] Tally otherwise
+static_assert(SM_NU % 8 == 0 && SM_SCAN % 8 == 0, "64-bit members need 8-byte offsets");
+constexpr size_t STREAM_SMEM_BUDGET = (227u * 1024u) / 2u - 1024u;            // two CTAs per SM, 1 KB per CTA reserved by the driver
 
-__host__ __device__ inline size_t stream_smem_bytes(int P, int nEn_hist) {
-  return (SM_TALLY + static_cast<size_t>(P) * sizeof(Tally) + static_cast<size_t>(nEn_hist) * 4 + 15) & ~static_cast<size_t>(15);
+__host__ __device__ inline bool stream_stages_nu(int P) { return SM_TALLY_STAGED + static_cast<size_t>(P) * sizeof(Tally) + 16 <= STREAM_SMEM_BUDGET; }
+__host__ __device__ inline size_t stream_smem_bytes(int P) {
+  return ((stream_stages_nu(P) ? SM_TALLY_STAGED : SM_TALLY_PLAIN) + static_cast<size_t>(P) * sizeof(Tally) + 15) & ~static_cast<size_t>(15);
 }
 
 struct StateId { State s; unsigned long long* id; };   // the 8 columns of s are one allocation: column c starts at s.x + c * n
@@ -95,12 +103,16 @@ __device__ __forceinline__ void tally_collisions_fx(int chosen, double dE, Tally
 }
 
 // branch-free null test (BMC.C:1035-1053, like cold_null_test)
-__device__ __forceinline__ bool stream_null_test(const Model& m, const double* __restrict__ nu_tab, double eps, double nue, double u, double& Rnu, bool& clamped, bool& exceeded) {
+__device__ __forceinline__ bool stream_null_test(const Model& m, const double* s_nu, int staged_rows, double eps, double nue, double u, double& Rnu, bool& clamped, bool& exceeded) {
   Rnu = nue * u;
   int i1, i2; double w1, w2;
   cold_rows(m, eps, i1, i2, w1, w2);
   clamped = (i1 == m.nE - 1);
-  const double nu_here = w1 * __ldg(&nu_tab[i1]) + w2 * __ldg(&nu_tab[i2]);
+  // the staged rows are read from shared memory, the rest from global: one generic load per row, no branch (the block stays straight-line)
+  const bool in_smem = i2 < staged_rows;
+  const double* p1 = in_smem ? s_nu + i1 : m.nu_tot + i1;
+  const double* p2 = in_smem ? s_nu + i2 : m.nu_tot + i2;
+  const double nu_here = w1 * *p1 + w2 * *p2;
   exceeded = nu_here > nue;
   return !(Rnu > nu_here);                                         // BMC.C:1050
 }
@@ -143,7 +155,8 @@ __global__ void __launch_bounds__(STREAM_THREADS, 2) k_advance_stream(const Mode
   unsigned char* flag = smem_raw + SM_FLAG;                                                 // [POOL]
   unsigned int* s_misc = reinterpret_cast<unsigned int*>(smem_raw + SM_MISC);               // [MC_COUNT]
   volatile int* s_rs = reinterpret_cast<volatile int*>(smem_raw + SM_RS);                   // [RS_COUNT] round state
-  Tally* s_tally = reinterpret_cast<Tally*>(smem_raw + SM_TALLY);                           // [P]
+  const double* s_nu = reinterpret_cast<const double*>(smem_raw + SM_NU);                   // [a.pad] first rows of nu_tot (a.pad = 0: not staged)
+  Tally* s_tally = reinterpret_cast<Tally*>(smem_raw + (a.pad ? SM_TALLY_STAGED : SM_TALLY_PLAIN));   // [P]
 
   {
   const int tid = tid_now();
@@ -152,6 +165,7 @@ __global__ void __launch_bounds__(STREAM_THREADS, 2) k_advance_stream(const Mode
   s_gf[tid] = 0;
   s_tmax[tid] = 0; s_tmax[STREAM_THREADS + tid] = 0;
   if (tid < MC_COUNT) s_misc[tid] = 0;
+  for (int j = tid; j < static_cast<int>(a.pad); j += STREAM_THREADS) reinterpret_cast<double*>(smem_raw + SM_NU)[j] = __ldg(&m.nu_tot[j]);
   reinterpret_cast<unsigned int*>(flag)[tid] = 0u;   // all slots FL_EMPTY
 
   // the CTA's range [lo, lo + len) of the ensemble; cursors are CTA-uniform offsets into it.  Column c of the state is sid.s.x + lo + c * a.n.
@@ -340,7 +354,7 @@ __global__ void __launch_bounds__(STREAM_THREADS, 2) k_advance_stream(const Mode
       const int nC = (cc - wrot + STREAM_WARPS - 1) >> 3;
       const int nR = (rc - warp + STREAM_WARPS - 1) >> 3;                                          // refill ranks [32 g, 32 g + 32), g = warp, warp + 8, ...: issued by these very threads
       const int nA = nK + nC, nItems = nA + nR;
-      const double* __restrict__ nu_tab = m.nu_tot;
+      const int staged_rows = static_cast<int>(a.pad);
       const double rnu = recip_for_div(a.nu_trial);
       bool waited = false;
 #pragma unroll 1
@@ -395,7 +409,7 @@ __global__ void __launch_bounds__(STREAM_THREADS, 2) k_advance_stream(const Mode
           f.gain = flight<FIELD>(m, p, dt);                          // one flight site for both outcomes (BMC.C:659, :666)
           const bool thermal = thermal_branch<GT>(m, p.eps);
           double Rnu; bool clamped, exceeded;
-          const bool real = stream_null_test(m, nu_tab, p.eps, p.nue, u_null, Rnu, clamped, exceeded);
+          const bool real = stream_null_test(m, s_nu, staged_rows, p.eps, p.nue, u_null, Rnu, clamped, exceeded);
           const bool tested = !partial && !thermal;                  // the thermal-target branch draws its own numbers in (3)
           f.outcome = partial ? FL_DONE : thermal ? FL_REALT : real ? FL_REAL : FL_FLIGHT;
           const double t_event = p.t + p.tcf;

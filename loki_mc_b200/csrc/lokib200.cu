@@ -193,14 +193,16 @@ int launch_advance(lokib200_engine* h, bool sample, const Model& m, const AdvArg
 
 template <int F, int G>
 int launch_stream_t(lokib200_engine* h, const Model& m, const AdvArgs& a, const HistGrid& hg) {
-  const size_t smem = stream_smem_bytes(h->P, 0);
+  const size_t smem = stream_smem_bytes(h->P);
+  AdvArgs as = a;
+  as.pad = stream_stages_nu(h->P) ? static_cast<unsigned int>(std::min(h->nE, NU_STAGE_ROWS)) : 0u;   // rows of nu_tot the kernel stages in shared memory
   if (h->stream_smem_set != smem) {   // (an engine uses one instantiation on one device)
     CK(cudaFuncSetAttribute(k_advance_stream<F, G, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     CK(cudaFuncSetAttribute(k_advance_stream<F, G, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     h->stream_smem_set = smem;
   }
   const StateId sid{h->st, h->d_id};   // the kernel addresses column c as st.x + c * n (one allocation, lokib200_create)
-  k_advance_stream<F, G, false><<<h->tile_blocks, STREAM_THREADS, smem, h->stream>>>(m, sid, h->lists, h->pend, a, hg, h->d_adv_part);
+  k_advance_stream<F, G, false><<<h->tile_blocks, STREAM_THREADS, smem, h->stream>>>(m, sid, h->lists, h->pend, as, hg, h->d_adv_part);
   return 0;
 }
 template <int F>
@@ -422,7 +424,7 @@ int lokib200_set_processes(lokib200_engine* h, const lokib200_process_soa* p) {
   // kernel choice: the streaming-pool kernel needs several pools per CTA to amortise its fill/drain; LOKIB200_KERNEL=thread|stream overrides
   h->use_tile = h->cfg.n_electrons >= static_cast<int64_t>(4) * POOL * 2 * h->sm_count;
   if (const char* env = std::getenv("LOKIB200_KERNEL")) { if (!std::strcmp(env, "thread")) h->use_tile = false; else if (!std::strcmp(env, "stream") || !std::strcmp(env, "tile")) h->use_tile = true; }
-  if (stream_smem_bytes(P, 0) > 113 * 1024) h->use_tile = false;   // more than half an SM's shared memory: fall back
+  if (stream_smem_bytes(P) > STREAM_SMEM_BUDGET) h->use_tile = false;   // more than half an SM's shared memory: fall back to one electron per thread
   for (double** q : {&h->d_adv_part, &h->d_birth_part, &h->d_smp_part, &h->d_result}) if (*q) { cudaFree(*q); *q = nullptr; }
   if (h->h_result) { cudaFreeHost(h->h_result); h->h_result = nullptr; }
   CK(cudaMalloc(&h->d_adv_part, static_cast<size_t>(std::max(h->adv_blocks, h->tile_blocks)) * h->part_len * sizeof(double)));
