@@ -10,8 +10,17 @@ import subprocess
 import sys
 
 
+_SASS = {}
+
+
+def sass(path):
+    if path not in _SASS:
+        _SASS[path] = subprocess.run(["cuobjdump", "-sass", path], stdout=subprocess.PIPE, text=True).stdout
+    return _SASS[path]
+
+
 def scan(path):
-    out = subprocess.run(["cuobjdump", "-sass", path], stdout=subprocess.PIPE, text=True).stdout
+    out = sass(path)
     func, window, bad = None, {}, []
     ins = re.compile(r"/\*([0-9a-f]{4,})\*/\s+(.*?);")
     for line in out.split("\n"):
@@ -46,7 +55,7 @@ def scan_derived_bases(path, kernel="k_advance_stream"):
     """Second fault seen with the same ptxas: a uniform register holding `shared base + 16 P` (an array whose offset depended on the
     process count) was later used as the plain base.  The streaming kernel now keeps every shared array at a compile-time offset, so
     its SASS must contain no uniform LEA other than the base computation itself (ULEA URx, URcga, URx, 0x18)."""
-    out = subprocess.run(["cuobjdump", "-sass", path], stdout=subprocess.PIPE, text=True).stdout
+    out = sass(path)
     func, bad = None, []
     for line in out.split("\n"):
         if "Function :" in line:
