@@ -23,9 +23,16 @@ def _ref(name):
     return json.load(open(os.path.join(gio.GOLDEN_DIR, "ensemble_%s.json" % name)))
 
 
-@pytest.mark.parametrize("name", CASES)
-def test_swarm_parameters_within_3_sigma(name):
+# the same whole jobs with the streaming-pool kernel forced (at these ensemble sizes the engine would pick one electron per thread): the
+# production kernel of the large-ensemble benchmark must reproduce the reference's swarm parameters too, including births and deaths
+STREAM_CASES = ["reid_acb", "n2_aniso", "o2_sdcs", "arhe", "ls_att_aniso"]
+
+
+@pytest.mark.parametrize("name,kernel", [(c, "auto") for c in CASES] + [(c, "stream") for c in STREAM_CASES])
+def test_swarm_parameters_within_3_sigma(name, kernel, monkeypatch):
     import loki_mc_b200 as lk
+    if kernel != "auto":
+        monkeypatch.setenv("LOKIB200_KERNEL", kernel)
     g = gio.load(name)
     ref = _ref(name)
     n = 10 * ref["n_electrons"]
