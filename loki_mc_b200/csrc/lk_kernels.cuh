@@ -325,15 +325,33 @@ __global__ void __launch_bounds__(ADV_THREADS) k_sample(const State s, long long
   double val[N_SAMPLE_SUMS];
 #pragma unroll
   for (int j = 0; j < N_SAMPLE_SUMS; ++j) val[j] = 0;
-  for (long long i = blockIdx.x * static_cast<long long>(ADV_THREADS) + threadIdx.x; i < n; i += static_cast<long long>(gridDim.x) * ADV_THREADS) {
+  // two electrons per iteration: twelve 8-byte streaming loads in flight per thread (six were not enough to cover HBM latency at 16 warps/SM:
+  // 4.5 TB/s in profiles/r1_v17_launches.csv)
+  const long long stride = static_cast<long long>(gridDim.x) * ADV_THREADS;
+  for (long long i = blockIdx.x * static_cast<long long>(ADV_THREADS) + threadIdx.x; i < n; i += 2 * stride) {
+    const long long i2 = i + stride;
+    const bool two = i2 < n;
+    const long long j2 = two ? i2 : i;
     const double x = __ldcs(&s.x[i]), y = __ldcs(&s.y[i]), z = __ldcs(&s.z[i]), vx = __ldcs(&s.vx[i]), vy = __ldcs(&s.vy[i]), vz = __ldcs(&s.vz[i]);
-    const double eps = kinetic_eV(vx, vy, vz);
-    max_end = fmax(max_end, eps);
-    val[0] += eps; val[1] += x; val[2] += y; val[3] += z; val[4] += vx; val[5] += vy; val[6] += vz;
-    val[7] += x * x; val[8] += x * y; val[9] += x * z; val[11] += y * y; val[12] += y * z; val[15] += z * z;
-    val[16] += x * vx; val[17] += x * vy; val[18] += x * vz; val[19] += y * vx; val[20] += y * vy; val[21] += y * vz;
-    val[22] += z * vx; val[23] += z * vy; val[24] += z * vz; val[25] += 1.0;
-    if (h.enabled) sample_histograms(h, vx, vy, vz, eps, s_eeh);
+    const double xb = __ldcs(&s.x[j2]), yb = __ldcs(&s.y[j2]), zb = __ldcs(&s.z[j2]), vxb = __ldcs(&s.vx[j2]), vyb = __ldcs(&s.vy[j2]), vzb = __ldcs(&s.vz[j2]);
+    {
+      const double eps = kinetic_eV(vx, vy, vz);
+      max_end = fmax(max_end, eps);
+      val[0] += eps; val[1] += x; val[2] += y; val[3] += z; val[4] += vx; val[5] += vy; val[6] += vz;
+      val[7] += x * x; val[8] += x * y; val[9] += x * z; val[11] += y * y; val[12] += y * z; val[15] += z * z;
+      val[16] += x * vx; val[17] += x * vy; val[18] += x * vz; val[19] += y * vx; val[20] += y * vy; val[21] += y * vz;
+      val[22] += z * vx; val[23] += z * vy; val[24] += z * vz; val[25] += 1.0;
+      if (h.enabled) sample_histograms(h, vx, vy, vz, eps, s_eeh);
+    }
+    if (two) {
+      const double eps = kinetic_eV(vxb, vyb, vzb);
+      max_end = fmax(max_end, eps);
+      val[0] += eps; val[1] += xb; val[2] += yb; val[3] += zb; val[4] += vxb; val[5] += vyb; val[6] += vzb;
+      val[7] += xb * xb; val[8] += xb * yb; val[9] += xb * zb; val[11] += yb * yb; val[12] += yb * zb; val[15] += zb * zb;
+      val[16] += xb * vxb; val[17] += xb * vyb; val[18] += xb * vzb; val[19] += yb * vxb; val[20] += yb * vyb; val[21] += yb * vzb;
+      val[22] += zb * vxb; val[23] += zb * vyb; val[24] += zb * vzb; val[25] += 1.0;
+      if (h.enabled) sample_histograms(h, vxb, vyb, vzb, eps, s_eeh);
+    }
   }
 #pragma unroll
   for (int j = 0; j < N_SAMPLE_SUMS; ++j) {
