@@ -87,10 +87,17 @@ __device__ __forceinline__ void tally_collisions_fx(int chosen, double dE, Tally
     const unsigned peers = __match_any_sync(rm, chosen);
     const long long q = __double2ll_rn(dE * TALLY_SCALE);
     const unsigned long long g = (q > 0) ? static_cast<unsigned long long>(q) : 0ull, l = (q < 0) ? static_cast<unsigned long long>(-q) : 0ull;
-    const unsigned g0 = __reduce_add_sync(peers, static_cast<unsigned>(g & 0x1FFFFFu)), g1 = __reduce_add_sync(peers, static_cast<unsigned>((g >> 21) & 0x1FFFFFu)),
-                   g2 = __reduce_add_sync(peers, static_cast<unsigned>(g >> 42));
-    const unsigned l0 = __reduce_add_sync(peers, static_cast<unsigned>(l & 0x1FFFFFu)), l1 = __reduce_add_sync(peers, static_cast<unsigned>((l >> 21) & 0x1FFFFFu)),
-                   l2 = __reduce_add_sync(peers, static_cast<unsigned>(l >> 42));
+    // a side nobody in the warp contributes to (gains, in a batch of cold-gas collisions without superelastics) is skipped for the whole warp
+    const bool any_gain = __any_sync(rm, g != 0), any_loss = __any_sync(rm, l != 0);
+    unsigned g0 = 0, g1 = 0, g2 = 0, l0 = 0, l1 = 0, l2 = 0;
+    if (any_gain) {
+      g0 = __reduce_add_sync(peers, static_cast<unsigned>(g & 0x1FFFFFu)); g1 = __reduce_add_sync(peers, static_cast<unsigned>((g >> 21) & 0x1FFFFFu));
+      g2 = __reduce_add_sync(peers, static_cast<unsigned>(g >> 42));
+    }
+    if (any_loss) {
+      l0 = __reduce_add_sync(peers, static_cast<unsigned>(l & 0x1FFFFFu)); l1 = __reduce_add_sync(peers, static_cast<unsigned>((l >> 21) & 0x1FFFFFu));
+      l2 = __reduce_add_sync(peers, static_cast<unsigned>(l >> 42));
+    }
     if (lane == __ffs(peers) - 1) {
       Tally* t = s_tally + chosen;
       atomicAdd(&t->cnt, static_cast<unsigned int>(__popc(peers)));
