@@ -364,6 +364,7 @@ __global__ void __launch_bounds__(STREAM_THREADS, 2) k_advance_stream(const Mode
       const int staged_rows = static_cast<int>(a.pad);
       const double rnu = recip_for_div(a.nu_trial);
       bool waited = false;
+      double gain_round = 0, seen_round = 0;   // folded into the per-thread shared slots once per round
 #pragma unroll 1
       for (int it = 0; 2 * it < nItems; ++it) {
         if (!waited && 2 * it + 1 >= nA) { cp_async_wait_all(); waited = true; }   // this pair holds a refilled chunk: this thread's copies have landed (only it reads them)
@@ -432,7 +433,7 @@ __global__ void __launch_bounds__(STREAM_THREADS, 2) k_advance_stream(const Mode
           const Flyer& f = e[j];
           if (f.active) {
             const int sl = f.sl;
-            s_gf[tid] += f.gain;
+            gain_round += f.gain;
             col[SC_X * POOL + sl] = f.p.x; col[SC_Y * POOL + sl] = f.p.y; col[SC_Z * POOL + sl] = f.p.z;
             col[SC_VX * POOL + sl] = f.p.vx; col[SC_VY * POOL + sl] = f.p.vy; col[SC_VZ * POOL + sl] = f.p.vz;
             col[SC_TCF * POOL + sl] = f.p.tcf; col[SC_NUE * POOL + sl] = f.p.nue; col[SC_T * POOL + sl] = f.p.t;
@@ -444,8 +445,10 @@ __global__ void __launch_bounds__(STREAM_THREADS, 2) k_advance_stream(const Mode
 #pragma unroll
           for (int j = 0; j < 2; ++j) { if (e[j].clamped) atomicAdd(&s_misc[MC_CLAMP], 1u); if (e[j].exceeded) atomicAdd(&s_misc[MC_NUEX], 1u); }
         }
-        s_tmax[STREAM_THREADS + tid] = fmax(s_tmax[STREAM_THREADS + tid], seen);
+        seen_round = fmax(seen_round, seen);
       }
+      s_gf[tid] += gain_round;
+      s_tmax[STREAM_THREADS + tid] = fmax(s_tmax[STREAM_THREADS + tid], seen_round);
       if (!waited) cp_async_wait_all();
     }
     __syncthreads();
