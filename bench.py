@@ -170,7 +170,7 @@ def run_reference_arm(args):
         mean_e = r[0]
     value = events / elapsed
     line.update(value=value, ms_per_step=1e3 * elapsed / n_int,
-                config=dict(workload="N2 DC 100 Td anisotropic (configs[1] point), reference CPU path", model=args.model, electrons=n_ref,
+                config=dict(workload="N2 DC 100 Td anisotropic (configs[1] point), reference CPU path", process_set=args.model, electrons=n_ref,
                             sync_factor=1.0, intervals=n_int, mean_energy_eV=mean_e),
                 cpu_baseline=dict(value=value, unit="events/s", cores=cores, kind=kind, sample=sample),
                 e2e=dict(value=value, unit="events/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
@@ -384,7 +384,7 @@ def main():
             metric="collision_events_per_sec", value=ev_dev / (ms_dev * 1e-3), unit="events/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
             ms_per_step=ms_dev / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64", data="synthetic",
             config=dict(workload="N2 DC E/N=100 Td anisotropic scattering, 1e7 electrons per GPU, reference cadence (sync factor 1, ensemble sums every interval) [BASELINE.json configs[1]]",
-                        model=args.model, electrons_per_gpu=n, processes=P, sync_factor=1.0, relax_intervals=args.relax,
+                        process_set=args.model, electrons_per_gpu=n, processes=P, sync_factor=1.0, relax_intervals=args.relax,
                         mean_energy_eV=mean_energy_now, nu_trial=nu, table_mib=round(eng.table_info()["nE"] * ((P + 15) // 16 * 16) * 8 / 2 ** 20, 1),
                         l2_policy="state 640 MB per GPU >> 126 MB L2: every step streams it from HBM", intervals_per_collective=K, real_fraction=float(final[R.N_REAL] / (final[R.N_REAL] + final[R.N_NULL]))),
             e2e=dict(value=ev_e2e / (ms_e2e * 1e-3), unit="events/s", h2d_bytes_per_step=16 * world,
