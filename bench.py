@@ -385,7 +385,7 @@ def main():
             ms_per_step=ms_dev / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64", data="synthetic",
             config=dict(workload="N2 DC E/N=100 Td anisotropic scattering, 1e7 electrons per GPU, reference cadence (sync factor 1, ensemble sums every interval) [BASELINE.json configs[1]]",
                         process_set=args.model, electrons_per_gpu=n, processes=P, sync_factor=1.0, relax_intervals=args.relax,
-                        mean_energy_eV=mean_energy_now, nu_trial=nu, table_mib=round(eng.table_info()["nE"] * ((P + 15) // 16 * 16) * 8 / 2 ** 20, 1),
+                        mean_energy_eV=mean_energy_now, nu_trial=nu, table_mib=round(eng.table_info()["nE"] * ((P + 15) // 16 * 16) * 8 * 3 / 2 ** 20, 1),   # cumulative table (8 B / entry) + its row-pair form (16 B / entry)
                         l2_policy="state 640 MB per GPU >> 126 MB L2: every step streams it from HBM", intervals_per_collective=K, real_fraction=float(final[R.N_REAL] / (final[R.N_REAL] + final[R.N_NULL]))),
             e2e=dict(value=ev_e2e / (ms_e2e * 1e-3), unit="events/s", h2d_bytes_per_step=16 * world,
                      d2h_bytes_per_step=8 * L * world, ms_per_step=ms_e2e / args.steps),
