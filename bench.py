@@ -294,9 +294,10 @@ def main():
         nonlocal nu, mx
         nu = eng.check_nu_trial(mx, nu, horizon=11.0)
         t += 1.0 / nu
-        res = eng.advance(nu, t, sample=True)
-        if world > 1:
-            d_buf[0].copy_(torch.from_numpy(res)); combine(d_buf[0]); res = d_res.cpu().numpy()
+        if world > 1:   # the result vector stays on the device until the ranks have combined it: one collective, one device -> host read per interval
+            eng.advance_device(nu, t, True, d_buf[0].data_ptr()); combine(d_buf[0]); res = d_res.cpu().numpy()
+        else:
+            res = eng.advance(nu, t, sample=True)
         mx = max(res[R.MAX_EPS], res[R.MAX_EPS_SEEN])
         return t, res
 
