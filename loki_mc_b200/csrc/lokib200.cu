@@ -431,7 +431,7 @@ int lokib200_set_processes(lokib200_engine* h, const lokib200_process_soa* p) {
   CK(cudaMalloc(&h->d_birth_part, static_cast<size_t>(h->birth_blocks) * h->part_len * sizeof(double)));
   CK(cudaMalloc(&h->d_smp_part, static_cast<size_t>(h->smp_blocks) * h->part_len * sizeof(double)));
   CK(cudaMalloc(&h->d_result, h->part_len * sizeof(double)));
-  CK(cudaMallocHost(&h->h_result, h->part_len * sizeof(double)));
+  CK(cudaMallocHost(&h->h_result, (h->part_len + 2) * sizeof(double)));   // + the two population-control words (pinned: a pageable target would make the copy synchronous)
 
   // birth/death lists (only when a non-conservative channel exists)
   Lists& L = h->lists;
@@ -671,8 +671,9 @@ int lokib200_read_result(lokib200_engine* h, double* result) {
   if (!h || !h->d_result) return LOKIB200_ERR_INVALID;
   CK(cudaSetDevice(h->cfg.device));
   CK(cudaMemcpyAsync(h->h_result, h->d_result, h->part_len * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-  double pc[2] = {0, 0};
-  if (h->has_pc) CK(cudaMemcpyAsync(pc, h->d_pc_result, sizeof(pc), cudaMemcpyDeviceToHost, h->stream));
+  double* pc = h->h_result + h->part_len;
+  pc[0] = 0; pc[1] = 0;
+  if (h->has_pc) CK(cudaMemcpyAsync(pc, h->d_pc_result, 2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
   if (result) std::memcpy(result, h->h_result, h->part_len * sizeof(double));
   if (pc[1] != 0) return fail(h, LOKIB200_ERR_OVERFLOW, "birth/death list overflow inside one synchronisation interval");
