@@ -870,20 +870,21 @@ int lokib200_measure_fp64_peak(lokib200_engine* h, double* tflops) {
   if (!h || !tflops) return LOKIB200_ERR_INVALID;
   CK(cudaSetDevice(h->cfg.device));
   const int blocks = h->sm_count * 8, threads = 256, iters = 4096;
-  double* d_out = nullptr;
-  CK(cudaMalloc(&d_out, sizeof(double) * blocks));
-  cudaEvent_t e0, e1;
-  CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  struct Scratch {   // released on every return path
+    double* d_out = nullptr; cudaEvent_t e0 = nullptr, e1 = nullptr;
+    ~Scratch() { if (e0) cudaEventDestroy(e0); if (e1) cudaEventDestroy(e1); if (d_out) cudaFree(d_out); }
+  } sc;
+  CK(cudaMalloc(&sc.d_out, sizeof(double) * blocks));
+  CK(cudaEventCreate(&sc.e0)); CK(cudaEventCreate(&sc.e1));
   float best = 1e30f;
   for (int rep = 0; rep < 5; ++rep) {
-    CK(cudaEventRecord(e0, h->stream));
-    k_dfma_peak<<<blocks, threads, 0, h->stream>>>(d_out, iters, 1.0000001);
-    CK(cudaEventRecord(e1, h->stream));
+    CK(cudaEventRecord(sc.e0, h->stream));
+    k_dfma_peak<<<blocks, threads, 0, h->stream>>>(sc.d_out, iters, 1.0000001);
+    CK(cudaEventRecord(sc.e1, h->stream));
     CK(cudaStreamSynchronize(h->stream));
-    float ms = 0; CK(cudaEventElapsedTime(&ms, e0, e1));
+    float ms = 0; CK(cudaEventElapsedTime(&ms, sc.e0, sc.e1));
     if (rep > 0 && ms < best) best = ms;
   }
-  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d_out);
   *tflops = 2.0 * 16.0 * static_cast<double>(iters) * threads * blocks / (best * 1e-3) / 1e12;
   return 0;
 }
