@@ -172,6 +172,15 @@ MODELS = {
     "reid_b": (dict(lxcat=["ReidRampGas/ReidRampGas_LXCat.txt"], gasprops=REID_GAS, stateprops=REID_STATE, BN=200, angle=90), 10.0, (1e-3, 9.0)),
     "reid_ecr": (dict(lxcat=["ReidRampGas/ReidRampGas_LXCat.txt"], gasprops=REID_GAS, stateprops=REID_STATE, freq="800E6", angle=60, BN=ECR_B), 10.0, (1e-3, 9.0)),
     "reid_acb": (dict(lxcat=["ReidRampGas/ReidRampGas_LXCat.txt"], gasprops=REID_GAS, stateprops=REID_STATE, freq="800E6", angle=45, BN=1000), 10.0, (1e-3, 9.0)),
+    # the four non-DC field branches (BMC.C:816-897) x the two thermal-target modes (BMC.C:916): every instantiation of the advance kernels
+    "reid_ac_true": (dict(lxcat=["ReidRampGas/ReidRampGas_LXCat.txt"], gasprops=REID_GAS, stateprops=REID_STATE, freq="800E6", gastemp="true"), 10.0, (1e-3, 9.0)),
+    "reid_ac_smart": (dict(lxcat=["ReidRampGas/ReidRampGas_LXCat.txt"], gasprops=REID_GAS, stateprops=REID_STATE, freq="800E6", gastemp="smartActivation"), 10.0, (1e-3, 9.0)),
+    "reid_b_true": (dict(lxcat=["ReidRampGas/ReidRampGas_LXCat.txt"], gasprops=REID_GAS, stateprops=REID_STATE, BN=200, angle=90, gastemp="true"), 10.0, (1e-3, 9.0)),
+    "reid_b_smart": (dict(lxcat=["ReidRampGas/ReidRampGas_LXCat.txt"], gasprops=REID_GAS, stateprops=REID_STATE, BN=200, angle=90, gastemp="smartActivation"), 10.0, (1e-3, 9.0)),
+    "reid_ecr_true": (dict(lxcat=["ReidRampGas/ReidRampGas_LXCat.txt"], gasprops=REID_GAS, stateprops=REID_STATE, freq="800E6", angle=60, BN=ECR_B, gastemp="true"), 10.0, (1e-3, 9.0)),
+    "reid_ecr_smart": (dict(lxcat=["ReidRampGas/ReidRampGas_LXCat.txt"], gasprops=REID_GAS, stateprops=REID_STATE, freq="800E6", angle=60, BN=ECR_B, gastemp="smartActivation"), 10.0, (1e-3, 9.0)),
+    "reid_acb_true": (dict(lxcat=["ReidRampGas/ReidRampGas_LXCat.txt"], gasprops=REID_GAS, stateprops=REID_STATE, freq="800E6", angle=45, BN=1000, gastemp="true"), 10.0, (1e-3, 9.0)),
+    "reid_acb_smart": (dict(lxcat=["ReidRampGas/ReidRampGas_LXCat.txt"], gasprops=REID_GAS, stateprops=REID_STATE, freq="800E6", angle=45, BN=1000, gastemp="smartActivation"), 10.0, (1e-3, 9.0)),
     "reid_true_aniso": (dict(lxcat=["ReidRampGas/ReidRampGas_LXCat.txt"], gasprops=REID_GAS, stateprops=REID_STATE, gastemp="true", aniso=REID_ANISO), 4.0, (1e-3, 3.5)),
     "o2_sdcs": (dict(lxcat=["Oxygen/O2_LXCat.txt", "Oxygen/O2_rot_LXCat.txt"], gasprops=DB + "    fraction:\n      - O2 = 1\n", stateprops=O2_STATE,
                      ioniz="usingSDCS", gastemp="smartActivation", EN=50), 120.0, (1e-3, 110.0)),

@@ -6,6 +6,10 @@ import numpy as np
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 MODELS = ["reid_dc", "reid_ac", "reid_b", "reid_ecr", "reid_acb", "reid_true_aniso", "o2_sdcs", "n2_aniso", "n2_true_acb",
           "arhe", "arhe_true", "air", "ls_f05", "ls_att_aniso"]
+# the four non-DC field branches x {gasTemperatureEffect true, smartActivation}: with the models above, all 15 instantiations
+# (5 field cases x 3 thermal modes) of the advance kernels are covered
+FIELD_GT_MODELS = ["reid_%s_%s" % (f, t) for f in ("ac", "b", "ecr", "acb") for t in ("true", "smart")]
+MODELS += FIELD_GT_MODELS
 
 
 def load(name):

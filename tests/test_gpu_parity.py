@@ -95,7 +95,7 @@ def test_step_injected_matches_reference(gm):
     eng.close()
 
 
-NO_PC_MODELS = ["reid_dc", "reid_ac", "reid_b", "reid_ecr", "reid_acb", "reid_true_aniso"]
+NO_PC_MODELS = ["reid_dc", "reid_ac", "reid_b", "reid_ecr", "reid_acb", "reid_true_aniso"] + gio.FIELD_GT_MODELS
 
 
 def _start_state(g, n, rng, e_lo, e_hi):
@@ -106,7 +106,7 @@ def _start_state(g, n, rng, e_lo, e_hi):
     return np.vstack([r, v, np.full((1, n), -123456789.0), np.zeros((1, n))])
 
 
-@pytest.mark.parametrize("name", NO_PC_MODELS + ["n2_aniso", "arhe_true", "air"])
+@pytest.mark.parametrize("name", NO_PC_MODELS + ["n2_aniso", "n2_true_acb", "arhe_true", "air"])
 def test_interval_matches_oracle_per_electron(name):
     """three synchronisation intervals of a 4096-electron ensemble with the shared counter-based draw streams:
     every electron must follow the oracle's trajectory (energies kept below any ionization/attachment threshold so that the
@@ -273,7 +273,8 @@ def test_full_size_energy_balance(name, n):
 
 @pytest.mark.parametrize("name,e_hi,maxE", [("reid_dc", 5.0, 12.0), ("reid_ac", 5.0, 12.0), ("reid_b", 5.0, 12.0), ("reid_ecr", 5.0, 12.0),
                                              ("reid_acb", 5.0, 12.0), ("reid_true_aniso", 3.0, 8.0), ("n2_aniso", 60.0, 150.0),
-                                             ("arhe_true", 60.0, 150.0), ("air", 40.0, 100.0), ("ls_att_aniso", 40.0, 100.0)])
+                                             ("arhe_true", 60.0, 150.0), ("air", 40.0, 100.0), ("ls_att_aniso", 40.0, 100.0),
+                                             ("n2_true_acb", 30.0, 60.0)] + [(nm, 5.0, 12.0) for nm in gio.FIELD_GT_MODELS])
 def test_tile_kernel_equals_thread_kernel(name, e_hi, maxE, monkeypatch):
     """the shared-memory tile kernel (compacted event rounds) and the one-thread-per-electron kernel consume the same per-electron
     draw streams, so they must produce the same ensemble bit for bit and the same event counters -- also when electrons are

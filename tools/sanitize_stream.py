@@ -12,12 +12,13 @@ import numpy as np  # noqa: E402
 import golden_io as gio  # noqa: E402
 import test_gpu_parity as T  # noqa: E402
 
-models = sys.argv[1:] or ["n2_aniso", "air", "arhe_true", "reid_ac", "reid_b", "reid_ecr", "reid_acb", "ls_att_aniso", "reid_true_aniso", "o2_sdcs"]
+models = sys.argv[1:] or (["n2_aniso", "air", "arhe_true", "reid_ac", "reid_b", "reid_ecr", "reid_acb", "ls_att_aniso", "reid_true_aniso", "o2_sdcs", "n2_true_acb"]
+                          + gio.FIELD_GT_MODELS)
 for name in models:
     g = gio.load(name)
     n = 160_077
     rng = np.random.default_rng(5)
-    hot = name in ("n2_aniso", "air", "arhe_true", "ls_att_aniso", "o2_sdcs")
+    hot = name in ("n2_aniso", "air", "arhe_true", "ls_att_aniso", "o2_sdcs", "n2_true_acb")
     s0 = T._start_state(g, n, rng, 1e-2, 40.0 if hot else 5.0)
     eng = T._engine(g, n, seed=77, first_electron_id=3)
     eng.build_tables(100.0 if hot else 12.0)
