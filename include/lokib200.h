@@ -16,7 +16,7 @@
 extern "C" {
 #endif
 
-#define LOKIB200_ABI_VERSION 1
+#define LOKIB200_ABI_VERSION 2
 #define LOKIB200_NON_DEF (-123456789.0)    /* Headers/Constant.h:23 */
 #define LOKIB200_NULL_COLLISION (-1)       /* Headers/GeneralDefinitions.h:39 */
 #define LOKIB200_PARTIAL_FLIGHT (-2)       /* Headers/GeneralDefinitions.h:40 */
@@ -105,7 +105,9 @@ enum {
   LOKIB200_R_SUM_COUNT = 34,   /* --- entries below combine with MAX, not SUM --- */
   LOKIB200_R_MAX_EPS = 34,     /* max energy at t_sync [eV] (BMC.C:721, :1426) */
   LOKIB200_R_MAX_EPS_SEEN = 35,/* max energy seen at any collision point inside the interval */
-  LOKIB200_R_HEADER = 36       /* followed by counts[P], gain[P], loss[P] (collisionCounters, energyGain/LossProcesses) : SUM */
+  LOKIB200_R_OVERFLOW = 36,    /* != 0: a birth / death / pending list overflowed inside the interval (the sums are then wrong); MAX-combined,
+                                  so the flag survives the all-reduce and every rank sees it */
+  LOKIB200_R_HEADER = 37       /* followed by counts[P], gain[P], loss[P] (collisionCounters, energyGain/LossProcesses) : SUM */
 };
 #define LOKIB200_RESULT_LEN(P) (LOKIB200_R_HEADER + 3 * (P))
 
@@ -168,8 +170,30 @@ int lokib200_advance_to_sync(lokib200_engine* h, double nu_trial, double t_sync,
 /* same, asynchronous: the result stays in device memory (`d_result`, >= LOKIB200_RESULT_LEN(P) doubles, caller-owned device
  * pointer, e.g. a torch tensor that is then all-reduced over NCCL); no host synchronisation */
 int lokib200_advance_to_sync_device(lokib200_engine* h, double nu_trial, double t_sync, int32_t sample, double* d_result);
-/* blocking read of the result of the last lokib200_advance_to_sync_device(..., d_result = NULL) call into host memory */
+/* blocking read of the result of the last lokib200_advance_to_sync_device(..., d_result = NULL) call into host memory; returns
+ * LOKIB200_ERR_OVERFLOW when the vector carries the overflow flag */
 int lokib200_read_result(lokib200_engine* h, double* result);
+
+/* --- multi-GPU: the one exchange of the path ---
+ * The ensemble shards by global electron id (lokib200_config.first_electron_id); tables are replicated; per sampling interval the
+ * result vectors of all shards are combined by ONE grouped NCCL all-reduce (SUM entries + MAX entries) on the engines' streams, in
+ * place in device memory, so that every rank holds the same combined vector and takes the same trial-frequency / table decisions.
+ * Histograms are combined once per job the same way.  NCCL is loaded at run time (libnccl.so.2; the copy a host process such as
+ * PyTorch has already loaded is reused).  The reference has no distributed backend (it is one OpenMP process, BMC.C:636). */
+#define LOKIB200_COMM_ID_BYTES 128
+int lokib200_comm_unique_id(void* id128);                                  /* ncclGetUniqueId: call on one rank, broadcast the 128 bytes */
+/* one engine per process (torchrun / mpirun): collective call on all ranks */
+int lokib200_comm_init_rank(lokib200_engine* h, const void* id128, int32_t rank, int32_t n_ranks);
+/* all n engines live in this process, one per device (what `lokimc_b200 SETUP` with LOKIB200_GPUS=n does): ncclCommInitAll */
+int lokib200_comm_init_all(lokib200_engine* const* engines, int32_t n);
+int lokib200_comm_destroy(lokib200_engine* h);
+int32_t lokib200_comm_size(const lokib200_engine* h);                      /* 1 without a communicator */
+/* all-reduce the result vectors the last advance / sample left on the device; `engines` are the LOCAL members of the communicator
+ * (all of them after lokib200_comm_init_all, the single one after lokib200_comm_init_rank); d_results[i] may name a caller-owned
+ * device vector per engine (NULL = the engine's own, which lokib200_read_result then returns).  Asynchronous on the engines' streams. */
+int lokib200_comm_allreduce_results(lokib200_engine* const* engines, int32_t n, double* const* d_results);
+/* all-reduce (SUM) the accumulated histogram counts; afterwards every rank's lokib200_fetch_histograms returns the global counts */
+int lokib200_comm_allreduce_histograms(lokib200_engine* const* engines, int32_t n);
 
 /* --- distributions (replaces: getTimeDependDistributions BMC.C:1492-1572, histogramCount / histogram2DCount MathFunctions.C:61-127) ---
  * grids are those of checkSteadyState (BMC.C:1862-1883): energy [0,max_eedf_energy], cos in [-1,1], v_r in [0,v_max], v_z in [-v_max,v_max] */
@@ -186,6 +210,9 @@ int lokib200_step_injected(lokib200_engine* h, int32_t n, const lokib200_electro
 /* ensemble sums of the CURRENT state without advancing (the t = 0 sample of evaluateEEDF, BMC.C:310); fills the SUM_EPS..N_SAMPLED
  * and MAX_EPS entries of `result`, zeroes the rest */
 int lokib200_sample_moments(lokib200_engine* h, double* result);
+/* same, asynchronous: the vector stays on the device (engine-owned), to be combined with lokib200_comm_allreduce_results and read
+ * with lokib200_read_result */
+int lokib200_sample_moments_device(lokib200_engine* h);
 /* getTimeDependDistributions' regrid (BMC.C:1497-1548): new energy grid [0,new_max_eedf_energy] for the EEDF / angular histograms
  * (the velocity grid is kept, as in the reference); the device accumulators restart from zero and the caller carries the
  * remapped old counts */
@@ -210,7 +237,8 @@ int lokib200_measure_fp64_peak(lokib200_engine* h, double* tflops);
  * (loki_mc_b200/host/boltzmann_mc.cpp).  It keeps the reference's control flow: checkMaxCollisionFrequency before every
  * interval, sampling every `sync_over_sampling` intervals, checkSteadyState (:1787-1893), checkStatisticalErrors (:1743-1767),
  * the stop criteria (:320-325) and the time averages (:1484-1741).  Several engines (one per GPU, disjoint electron-id ranges)
- * may be passed: their per-interval result vectors are summed on the host, which is all the exchange the path needs.
+ * may be passed: when they share a communicator (lokib200_comm_init_all / _init_rank) their per-interval result vectors are combined
+ * by one NCCL all-reduce per sampling interval, otherwise they are read back one by one and summed on the host.
  * ------------------------------------------------------------------------------------------------------------------------ */
 typedef struct lokib200_solve_controls {   /* numericsMC keys, BMC.h:262-365 (values already multiplied by nElectrons where the ctor does) */
   double n_integration_points;           /* requiredIntegrationPoints */

@@ -1,5 +1,6 @@
-"""python -m loki_mc_b200 SETUP_FILE [NUM_GPUS] -- the reference executable's command line (Sources/lokimc.C) on the GPU engine.
-Run from a directory that holds Input/; results go to Output/<output.folder>/."""
+"""python -m loki_mc_b200 SETUP_FILE [NUM_THREADS] -- the reference executable's command line (Sources/lokimc.C) on the GPU engine.
+Run from a directory that holds Input/; results go to Output/<output.folder>/.  NUM_THREADS is accepted for compatibility and has no
+effect; the number of GPUs a job is sharded over comes from the environment variable LOKIB200_GPUS (default 1)."""
 import os
 import sys
 
@@ -8,7 +9,7 @@ from . import LokiB200Error, build, lib_path, run_setup
 
 def main(argv):
     if len(argv) not in (2, 3):
-        print("usage: python -m loki_mc_b200 SETUP_FILE [NUM_GPUS]")
+        print("usage: [LOKIB200_GPUS=n] python -m loki_mc_b200 SETUP_FILE [NUM_THREADS]")
         return 2
     if not os.path.exists(lib_path()):
         build()
@@ -17,7 +18,7 @@ def main(argv):
     except OSError:
         pass
     try:
-        run_setup("Input", argv[1], "Output", n_devices=int(argv[2]) if len(argv) == 3 else 1)
+        run_setup("Input", argv[1], "Output", n_devices=max(1, int(os.environ.get("LOKIB200_GPUS", "1"))))
     except LokiB200Error as e:
         with open("errorLog.txt", "a") as f:
             f.write("Program stopped due to the following error:\n%s\n" % e)

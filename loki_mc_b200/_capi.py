@@ -20,7 +20,7 @@ class LokiB200Error(RuntimeError):
 class R:
     """indices of the result vector (LOKIB200_R_* in include/lokib200.h)"""
     N_REAL, N_NULL, N_BORN, N_ATTACHED, GAIN_FIELD, GROWTH, SUM_EPS, SUM_R, SUM_V, SUM_RR, SUM_RV = 0, 1, 2, 3, 4, 5, 6, 7, 10, 13, 22
-    N_SAMPLED, N_TABLE_CLAMPED, N_NU_EXCEEDED, SUM_COUNT, MAX_EPS, MAX_EPS_SEEN, HEADER = 31, 32, 33, 34, 34, 35, 36
+    N_SAMPLED, N_TABLE_CLAMPED, N_NU_EXCEEDED, SUM_COUNT, MAX_EPS, MAX_EPS_SEEN, OVERFLOW, HEADER = 31, 32, 33, 34, 34, 35, 36, 37
 
 
 def result_len(P):
@@ -145,7 +145,9 @@ SYMBOLS = ["lokib200_abi_version", "lokib200_device_count", "lokib200_create", "
            "lokib200_launch_count", "lokib200_kernel_time_ms", "lokib200_measure_fp64_peak", "lokib200_get_config", "lokib200_process_count", "lokib200_get_rel_densities",
            "lokib200_sample_moments", "lokib200_regrid_energy_histograms", "lokib200_read_result", "lokib200_job_create", "lokib200_job_solve", "lokib200_job_results",
            "lokib200_job_process_outputs", "lokib200_job_time_series", "lokib200_job_histograms", "lokib200_job_periodic",
-           "lokib200_job_periodic_diffusion", "lokib200_job_conditions", "lokib200_job_evdf_max_speed", "lokib200_job_last_error", "lokib200_job_destroy"]
+           "lokib200_job_periodic_diffusion", "lokib200_job_conditions", "lokib200_job_evdf_max_speed", "lokib200_job_last_error", "lokib200_job_destroy",
+           "lokib200_sample_moments_device", "lokib200_comm_unique_id", "lokib200_comm_init_rank", "lokib200_comm_init_all", "lokib200_comm_destroy",
+           "lokib200_comm_size", "lokib200_comm_allreduce_results", "lokib200_comm_allreduce_histograms"]
 # every symbol include/lokib200_host.h declares
 HOST_SYMBOLS = ["lokib200_setup_load", "lokib200_setup_destroy", "lokib200_setup_last_error", "lokib200_setup_job_count", "lokib200_setup_job_value",
                 "lokib200_setup_variable_condition", "lokib200_setup_processes", "lokib200_setup_config", "lokib200_setup_controls",
@@ -192,6 +194,14 @@ def lib():
     L.lokib200_kernel_time_ms.argtypes = [vp, c_dp, c_lp]
     L.lokib200_measure_fp64_peak.argtypes = [vp, c_dp]
     L.lokib200_sample_moments.argtypes = [vp, c_dp]
+    L.lokib200_sample_moments_device.argtypes = [vp]
+    L.lokib200_comm_unique_id.argtypes = [vp]
+    L.lokib200_comm_init_rank.argtypes = [vp, vp, C.c_int32, C.c_int32]
+    L.lokib200_comm_init_all.argtypes = [C.POINTER(vp), C.c_int32]
+    L.lokib200_comm_destroy.argtypes = [vp]
+    L.lokib200_comm_size.argtypes = [vp]; L.lokib200_comm_size.restype = C.c_int32
+    L.lokib200_comm_allreduce_results.argtypes = [C.POINTER(vp), C.c_int32, C.POINTER(vp)]
+    L.lokib200_comm_allreduce_histograms.argtypes = [C.POINTER(vp), C.c_int32]
     L.lokib200_regrid_energy_histograms.argtypes = [vp, C.c_double]
     L.lokib200_read_result.argtypes = [vp, c_dp]
     L.lokib200_get_config.argtypes = [vp, C.POINTER(Config)]
@@ -365,6 +375,34 @@ class Engine:
     def set_stream(self, stream_ptr):
         self._check(self.L.lokib200_set_stream(self.h, C.c_void_p(stream_ptr)))
 
+    def read_result(self):
+        res = np.zeros(result_len(self.P))
+        self._check(self.L.lokib200_read_result(self.h, _dp(res)))
+        return res
+
+    def sample_moments(self):
+        res = np.zeros(result_len(self.P))
+        self._check(self.L.lokib200_sample_moments(self.h, _dp(res)))
+        return res
+
+    # --- multi-GPU: shards of one job share a communicator (include/lokib200.h, "multi-GPU") ---
+    def comm_init_rank(self, unique_id, rank, n_ranks):
+        """one engine per process: `unique_id` = the 128 bytes of comm_unique_id() of rank 0, broadcast by the launcher"""
+        buf = (C.c_char * COMM_ID_BYTES).from_buffer_copy(bytes(unique_id))
+        self._check(self.L.lokib200_comm_init_rank(self.h, C.cast(buf, C.c_void_p), int(rank), int(n_ranks)))
+
+    def comm_size(self):
+        return int(self.L.lokib200_comm_size(self.h))
+
+    def comm_destroy(self):
+        self._check(self.L.lokib200_comm_destroy(self.h))
+
+    def allreduce_results(self, d_result_ptr=None):
+        """combine the result vector of the last advance_device / sample with all other ranks (asynchronous, on the engine's stream)"""
+        arr = (C.c_void_p * 1)(self.h)
+        ptrs = (C.c_void_p * 1)(C.c_void_p(d_result_ptr)) if d_result_ptr else None
+        self._check(self.L.lokib200_comm_allreduce_results(arr, 1, ptrs))
+
     def step_injected(self, electrons, nu_trial, t_sync, draws):
         e = np.ascontiguousarray(electrons, dtype=ELECTRON_DTYPE); n = len(e)
         d = np.ascontiguousarray(draws, dtype=np.float64); assert d.shape[0] == n
@@ -409,6 +447,32 @@ class Engine:
         v = C.c_double()
         self._check(self.L.lokib200_measure_fp64_peak(self.h, C.byref(v)))
         return v.value
+
+
+COMM_ID_BYTES = 128
+
+
+def comm_unique_id():
+    buf = (C.c_char * COMM_ID_BYTES)()
+    rc = lib().lokib200_comm_unique_id(C.cast(buf, C.c_void_p))
+    if rc != 0:
+        raise LokiB200Error("lokib200_comm_unique_id failed (%d): %s" % (rc, lib().lokib200_last_error(None).decode()))
+    return bytes(buf)
+
+
+def comm_init_all(engines):
+    """all engines live in this process, one per device: one communicator over them (ncclCommInitAll)"""
+    arr = (C.c_void_p * len(engines))(*[e.h for e in engines])
+    rc = lib().lokib200_comm_init_all(arr, len(engines))
+    if rc != 0:
+        raise LokiB200Error("lokib200_comm_init_all failed (%d): %s" % (rc, lib().lokib200_last_error(engines[0].h).decode()))
+
+
+def allreduce_results(engines):
+    arr = (C.c_void_p * len(engines))(*[e.h for e in engines])
+    rc = lib().lokib200_comm_allreduce_results(arr, len(engines), None)
+    if rc != 0:
+        raise LokiB200Error("lokib200_comm_allreduce_results failed (%d): %s" % (rc, lib().lokib200_last_error(engines[0].h).decode()))
 
 
 class Job:

@@ -25,7 +25,7 @@ constexpr unsigned FULL = 0xFFFFFFFFu;
 enum : int {
   R_N_REAL = 0, R_N_NULL = 1, R_N_BORN = 2, R_N_ATTACHED = 3, R_GAIN_FIELD = 4, R_GROWTH = 5, R_SUM_EPS = 6, R_SUM_R = 7, R_SUM_V = 10,
   R_SUM_RR = 13, R_SUM_RV = 22, R_N_SAMPLED = 31, R_N_TABLE_CLAMPED = 32, R_N_NU_EXCEEDED = 33, R_SUM_COUNT = 34, R_MAX_EPS = 34,
-  R_MAX_EPS_SEEN = 35, R_HEADER = 36
+  R_MAX_EPS_SEEN = 35, R_OVERFLOW = 36, R_HEADER = 37
 };
 constexpr int N_SAMPLE_SUMS = 26;        // R_SUM_EPS .. R_N_SAMPLED
 
@@ -483,6 +483,7 @@ __global__ void k_finalize(const double* __restrict__ adv_partials, int adv_bloc
   }
   v = is_max ? warp_max(v) : warp_sum(v);
   if (j == R_GROWTH && pc_result) v = pc_result[0];
+  if (j == R_OVERFLOW) v = pc_result ? pc_result[1] : 0.0;   // list overflow of this interval (k_pc_reset): travels with the vector, MAX-combined
   if (lane == 0) result[j] = v;
 }
 

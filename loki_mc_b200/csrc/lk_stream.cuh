@@ -324,6 +324,7 @@ __global__ void __launch_bounds__(STREAM_THREADS, 2) k_advance_stream(const Mode
           else chosen = cold_select(m, p, col[SC_TCF * POOL + sl]);
           if (chosen != NULL_COLLISION) chosen = collide_dynamics<GT>(m, chosen, p, Vx, Vy, Vz, rng, o);
           if (o.table_clamped) atomicAdd(&s_misc[MC_CLAMP], 1u);
+            if (o.nu_exceeded) atomicAdd(&s_misc[MC_NUEX], 1u);
           unsigned char outcome = FL_FLIGHT;
           if (chosen >= 0) {
             dE = o.dE;

@@ -6,6 +6,9 @@
 // when no CUDA device is usable.
 #include "../../include/lokib200.h"
 
+#include <dlfcn.h>
+#include <nccl.h>
+
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -21,7 +24,8 @@ using namespace lk;
 static_assert(LOKIB200_R_N_REAL == R_N_REAL && LOKIB200_R_GROWTH == R_GROWTH && LOKIB200_R_SUM_EPS == R_SUM_EPS && LOKIB200_R_SUM_RR == R_SUM_RR &&
               LOKIB200_R_SUM_RV == R_SUM_RV && LOKIB200_R_N_SAMPLED == R_N_SAMPLED && LOKIB200_R_MAX_EPS == R_MAX_EPS &&
               LOKIB200_R_MAX_EPS_SEEN == R_MAX_EPS_SEEN && LOKIB200_R_HEADER == R_HEADER && LOKIB200_R_SUM_COUNT == R_SUM_COUNT &&
-              LOKIB200_R_N_TABLE_CLAMPED == R_N_TABLE_CLAMPED && LOKIB200_R_N_NU_EXCEEDED == R_N_NU_EXCEEDED, "result layout");
+              LOKIB200_R_N_TABLE_CLAMPED == R_N_TABLE_CLAMPED && LOKIB200_R_N_NU_EXCEEDED == R_N_NU_EXCEEDED && LOKIB200_R_OVERFLOW == R_OVERFLOW,
+              "result layout");
 static_assert(sizeof(lokib200_electron) == sizeof(ElectronIO) && sizeof(lokib200_event_out) == sizeof(EventIO), "parity structs");
 
 static std::string g_create_error;
@@ -51,10 +55,9 @@ struct lokib200_engine {
   bool have_tables = false;
   std::vector<double> h_cum, h_nu_tot, h_nu_max;   // host copies (h_cum padded to stride)
   double *d_cum = nullptr, *d_nu_tot = nullptr;
-  double2 *d_pair = nullptr, *d_coarse = nullptr;   // row-pair form of the cumulative table + its coarse level (see lk_physics.cuh)
-  int G = 0, gstride = 0;
-  std::vector<double2> h_pair, h_coarse;
-  size_t d_cum_cap = 0;
+  double2* d_pair = nullptr;   // row-pair form of the cumulative table (see lk_physics.cuh)
+  std::vector<double2> h_pair;
+  size_t d_cum_cap = 0, d_nu_cap = 0;   // capacities (elements) of d_cum / d_pair and of d_nu_tot: each buffer is tracked on its own
 
   // ensemble
   State st{};
@@ -68,8 +71,15 @@ struct lokib200_engine {
   double *d_adv_part = nullptr, *d_birth_part = nullptr, *d_smp_part = nullptr, *d_result = nullptr, *d_pc_result = nullptr, *h_result = nullptr;
   unsigned long long* d_maxbits = nullptr;
   int adv_blocks = 0, tile_blocks = 0, birth_blocks = 0, smp_blocks = 0, part_len = 0;
-  bool use_tile = false;
+  bool use_tile = false;   // a shared-memory kernel (stream or lane) instead of one electron per thread
   int last_adv_blocks = 0;
+
+  // multi-GPU: communicator over the shards of one job (null = none)
+  ncclComm_t comm = nullptr;
+  int comm_size = 1, comm_rank = 0;
+  bool comm_local_group = false;   // created by lokib200_comm_init_all: collectives must be issued for all local engines in one NCCL group
+  unsigned long long* d_hist_red = nullptr;   // all-reduced copy of the four histogram arrays (the accumulators keep this rank's own counts)
+  bool hist_reduced = false;                  // d_hist_red holds the combined counts of the current accumulators
 
   // histograms
   HistGrid hist{};
@@ -83,7 +93,6 @@ struct lokib200_engine {
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pool;
   size_t ev_used = 0;
   bool timing = true;
-  size_t stream_smem_set = 0;   // dynamic shared memory the streaming kernel's attributes were last set for (0 = never)
 };
 
 namespace {
@@ -138,7 +147,7 @@ Model make_model(const lokib200_engine* h) {
     }
   }
   m.cum = h->d_cum; m.nu_tot = h->d_nu_tot;
-  m.pair = h->d_pair; m.coarse = h->d_coarse; m.G = h->G; m.gstride = h->gstride;
+  m.pair = h->d_pair;
   m.type = h->d_type; m.angular = h->d_angular; m.ap0 = h->d_ap0; m.ap1 = h->d_ap1; m.mass = h->d_mass; m.redmass = h->d_redmass;
   m.eloss = h->d_eloss; m.thstd = h->d_thstd; m.wpar = h->d_wpar; m.gas_first = h->d_gas_first; m.gas_last = h->d_gas_last;
   m.gas_fraction = h->d_gas_fraction;
@@ -196,10 +205,13 @@ int launch_stream_t(lokib200_engine* h, const Model& m, const AdvArgs& a, const 
   const size_t smem = stream_smem_bytes(h->P);
   AdvArgs as = a;
   as.pad = stream_stages_nu(h->P) ? static_cast<unsigned int>(std::min(h->nE, NU_STAGE_ROWS)) : 0u;   // rows of nu_tot the kernel stages in shared memory
-  if (h->stream_smem_set != smem) {   // (an engine uses one instantiation on one device)
-    CK(cudaFuncSetAttribute(k_advance_stream<F, G, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  // the limit belongs to the kernel and the device, not to the engine (two engines with different P share one instantiation): raise it to the
+  // budget once per instantiation and device, never lower it
+  static bool attr_set[64] = {};
+  if (!attr_set[h->cfg.device & 63]) {
+    CK(cudaFuncSetAttribute(k_advance_stream<F, G, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(STREAM_SMEM_BUDGET)));
     CK(cudaFuncSetAttribute(k_advance_stream<F, G, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    h->stream_smem_set = smem;
+    attr_set[h->cfg.device & 63] = true;
   }
   const StateId sid{h->st, h->d_id};   // the kernel addresses column c as st.x + c * n (one allocation, lokib200_create)
   k_advance_stream<F, G, false><<<h->tile_blocks, STREAM_THREADS, smem, h->stream>>>(m, sid, h->lists, h->pend, as, hg, h->d_adv_part);
@@ -266,6 +278,49 @@ void launch_injected_g(lokib200_engine* h, int gt, const Model& m, int n, const 
   }
 }
 
+// NCCL is bound at run time: a host process that already carries a copy (PyTorch ships its own libnccl.so.2) must see ONE instance
+struct NcclApi {
+  decltype(&ncclGetUniqueId) GetUniqueId = nullptr;
+  decltype(&ncclCommInitRank) CommInitRank = nullptr;
+  decltype(&ncclCommInitAll) CommInitAll = nullptr;
+  decltype(&ncclCommDestroy) CommDestroy = nullptr;
+  decltype(&ncclAllReduce) AllReduce = nullptr;
+  decltype(&ncclGroupStart) GroupStart = nullptr;
+  decltype(&ncclGroupEnd) GroupEnd = nullptr;
+  decltype(&ncclGetErrorString) GetErrorString = nullptr;
+  std::string why;
+  bool ok = false;
+};
+NcclApi* nccl_api() {
+  static NcclApi api;
+  static bool tried = false;
+  if (tried) return &api;
+  tried = true;
+  void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL);
+  if (!lib) lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  if (!lib) { api.why = std::string("cannot load libnccl.so.2: ") + dlerror(); return &api; }
+  auto sym = [&](const char* n) { void* p = dlsym(lib, n); if (!p) api.why = std::string("libnccl misses ") + n; return p; };
+  api.GetUniqueId = reinterpret_cast<decltype(api.GetUniqueId)>(sym("ncclGetUniqueId"));
+  api.CommInitRank = reinterpret_cast<decltype(api.CommInitRank)>(sym("ncclCommInitRank"));
+  api.CommInitAll = reinterpret_cast<decltype(api.CommInitAll)>(sym("ncclCommInitAll"));
+  api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(sym("ncclCommDestroy"));
+  api.AllReduce = reinterpret_cast<decltype(api.AllReduce)>(sym("ncclAllReduce"));
+  api.GroupStart = reinterpret_cast<decltype(api.GroupStart)>(sym("ncclGroupStart"));
+  api.GroupEnd = reinterpret_cast<decltype(api.GroupEnd)>(sym("ncclGroupEnd"));
+  api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(sym("ncclGetErrorString"));
+  api.ok = api.GetUniqueId && api.CommInitRank && api.CommInitAll && api.CommDestroy && api.AllReduce && api.GroupStart && api.GroupEnd && api.GetErrorString;
+  return &api;
+}
+#define NK(call)                                                                                                         \
+  do {                                                                                                                   \
+    ncclResult_t r_ = (call);                                                                                            \
+    if (r_ != ncclSuccess) {                                                                                             \
+      h->err = std::string(#call) + ": " + nc->GetErrorString(r_);                                                       \
+      return LOKIB200_ERR_CUDA;                                                                                          \
+    }                                                                                                                    \
+  } while (0)
+
 int ensure_ready(lokib200_engine* h, bool need_tables) {
   if (!h) return LOKIB200_ERR_INVALID;
   if (!h->have_processes) return fail(h, LOKIB200_ERR_INVALID, "lokib200_set_processes has not been called");
@@ -274,37 +329,32 @@ int ensure_ready(lokib200_engine* h, bool need_tables) {
 }
 
 int push_tables(lokib200_engine* h) {   // h_cum (padded) / h_nu_tot -> device
-  const size_t need = static_cast<size_t>(h->nE) * h->stride;
-  h->G = (h->P + 7) / 8; h->gstride = (h->G + 3) / 4 * 4;
-  const size_t need_c = static_cast<size_t>(h->nE) * h->gstride;
+  const size_t need = static_cast<size_t>(h->nE) * h->stride, need_nu = static_cast<size_t>(h->nE);
   if (need > h->d_cum_cap) {
-    for (void* q : {static_cast<void*>(h->d_cum), static_cast<void*>(h->d_nu_tot), static_cast<void*>(h->d_pair), static_cast<void*>(h->d_coarse)}) if (q) cudaFree(q);
+    if (h->d_cum) cudaFree(h->d_cum);
+    if (h->d_pair) cudaFree(h->d_pair);
+    h->d_cum = nullptr; h->d_pair = nullptr; h->d_cum_cap = 0;
     CK(cudaMalloc(&h->d_cum, need * sizeof(double)));
-    CK(cudaMalloc(&h->d_nu_tot, static_cast<size_t>(h->nE) * sizeof(double)));
-#if defined(LK_SELECT_2LEVEL) || !defined(LK_SELECT_SPLIT_ROWS)
     CK(cudaMalloc(&h->d_pair, need * sizeof(double2)));
-    CK(cudaMalloc(&h->d_coarse, need_c * sizeof(double2)));
-#else
-    h->d_pair = nullptr; h->d_coarse = nullptr;
-#endif
     h->d_cum_cap = need;
   }
-#if defined(LK_SELECT_2LEVEL) || !defined(LK_SELECT_SPLIT_ROWS)
-  // row-pair + coarse forms, derived from the same doubles (no arithmetic: the kernels see identical table values)
-  h->h_pair.resize(need); h->h_coarse.resize(need_c);
+  if (need_nu > h->d_nu_cap) {
+    if (h->d_nu_tot) cudaFree(h->d_nu_tot);
+    h->d_nu_tot = nullptr; h->d_nu_cap = 0;
+    CK(cudaMalloc(&h->d_nu_tot, need_nu * sizeof(double)));
+    h->d_nu_cap = need_nu;
+  }
+  // row-pair form, derived from the same doubles (no arithmetic: the kernels see identical table values)
+  h->h_pair.resize(need);
   for (int i = 0; i < h->nE; ++i) {
     const double* r1 = h->h_cum.data() + static_cast<size_t>(i) * h->stride;
     const double* r2 = h->h_cum.data() + static_cast<size_t>(std::min(i + 1, h->nE - 1)) * h->stride;
     double2* pr = h->h_pair.data() + static_cast<size_t>(i) * h->stride;
     for (int k = 0; k < h->stride; ++k) pr[k] = make_double2(r1[k], r2[k]);
-    double2* cr = h->h_coarse.data() + static_cast<size_t>(i) * h->gstride;
-    for (int g = 0; g < h->gstride; ++g) cr[g] = pr[std::min(8 * g + 7, h->stride - 1)];
   }
   CK(cudaMemcpyAsync(h->d_pair, h->h_pair.data(), need * sizeof(double2), cudaMemcpyHostToDevice, h->stream));
-  CK(cudaMemcpyAsync(h->d_coarse, h->h_coarse.data(), need_c * sizeof(double2), cudaMemcpyHostToDevice, h->stream));
-#endif
   CK(cudaMemcpyAsync(h->d_cum, h->h_cum.data(), need * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-  CK(cudaMemcpyAsync(h->d_nu_tot, h->h_nu_tot.data(), static_cast<size_t>(h->nE) * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(h->d_nu_tot, h->h_nu_tot.data(), need_nu * sizeof(double), cudaMemcpyHostToDevice, h->stream));
   CK(cudaStreamSynchronize(h->stream));
   h->have_tables = true;
   return 0;
@@ -364,10 +414,11 @@ void lokib200_destroy(lokib200_engine* h) {
   if (!h) return;
   cudaSetDevice(h->cfg.device);
   if (h->stream) cudaStreamSynchronize(h->stream);
+  if (h->comm) { NcclApi* nc = nccl_api(); if (nc->ok) nc->CommDestroy(h->comm); h->comm = nullptr; }
   void* ptrs[] = {h->d_type, h->d_angular, h->d_gas_first, h->d_gas_last, h->d_ap0, h->d_ap1, h->d_mass, h->d_redmass, h->d_eloss, h->d_thstd, h->d_wpar,
-                  h->d_gas_fraction, h->d_cum, h->d_nu_tot, h->d_pair, h->d_coarse, h->d_state, h->d_id, h->lists.birth, h->lists.dead, h->lists.freed, h->lists.claim, h->lists.dead_flag,
+                  h->d_gas_fraction, h->d_cum, h->d_nu_tot, h->d_pair, h->d_state, h->d_id, h->lists.birth, h->lists.dead, h->lists.freed, h->lists.claim, h->lists.dead_flag,
                   h->lists.growth_terms, h->lists.counters, h->pend.col, h->d_adv_part, h->d_birth_part, h->d_smp_part, h->d_result, h->d_pc_result, h->d_maxbits, h->d_eeh, h->d_eah,
-                  h->d_evh, h->d_eeh_per};
+                  h->d_evh, h->d_eeh_per, h->d_hist_red};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (h->h_result) cudaFreeHost(h->h_result);
   for (auto& pr : h->ev_pool) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
@@ -431,7 +482,7 @@ int lokib200_set_processes(lokib200_engine* h, const lokib200_process_soa* p) {
   CK(cudaMalloc(&h->d_birth_part, static_cast<size_t>(h->birth_blocks) * h->part_len * sizeof(double)));
   CK(cudaMalloc(&h->d_smp_part, static_cast<size_t>(h->smp_blocks) * h->part_len * sizeof(double)));
   CK(cudaMalloc(&h->d_result, h->part_len * sizeof(double)));
-  CK(cudaMallocHost(&h->h_result, (h->part_len + 2) * sizeof(double)));   // + the two population-control words (pinned: a pageable target would make the copy synchronous)
+  CK(cudaMallocHost(&h->h_result, (h->part_len + 2) * sizeof(double)));   // pinned: a pageable target would make the copy synchronous
 
   // birth/death lists (only when a non-conservative channel exists)
   Lists& L = h->lists;
@@ -671,22 +722,130 @@ int lokib200_read_result(lokib200_engine* h, double* result) {
   if (!h || !h->d_result) return LOKIB200_ERR_INVALID;
   CK(cudaSetDevice(h->cfg.device));
   CK(cudaMemcpyAsync(h->h_result, h->d_result, h->part_len * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-  double* pc = h->h_result + h->part_len;
-  pc[0] = 0; pc[1] = 0;
-  if (h->has_pc) CK(cudaMemcpyAsync(pc, h->d_pc_result, 2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
   if (result) std::memcpy(result, h->h_result, h->part_len * sizeof(double));
-  if (pc[1] != 0) return fail(h, LOKIB200_ERR_OVERFLOW, "birth/death list overflow inside one synchronisation interval");
+  if (h->h_result[R_OVERFLOW] != 0) return fail(h, LOKIB200_ERR_OVERFLOW, "birth/death list overflow inside one synchronisation interval (on this or another rank)");
   return 0;
 }
 
 int lokib200_advance_to_sync(lokib200_engine* h, double nu_trial, double t_sync, int32_t sample, double* result) {
   int rc = lokib200_advance_to_sync_device(h, nu_trial, t_sync, sample, nullptr);
   if (rc) return rc;
+  if (h->comm) {   // shards of one job: every rank returns the combined vector
+    if (h->comm_local_group) return fail(h, LOKIB200_ERR_INVALID, "engines of one process share a communicator: advance them with lokib200_advance_to_sync_device and combine with lokib200_comm_allreduce_results");
+    lokib200_engine* one[1] = {h};
+    if ((rc = lokib200_comm_allreduce_results(one, 1, nullptr))) return rc;
+  }
   return lokib200_read_result(h, result);
 }
 
-int lokib200_sample_moments(lokib200_engine* h, double* result) {
+// ---------------------------------------------------------------- multi-GPU exchange ----------------------------------------------------------------
+int lokib200_comm_unique_id(void* id128) {
+  NcclApi* nc = nccl_api();
+  if (!id128 || !nc->ok) { g_create_error = nc->ok ? "null argument" : nc->why; return nc->ok ? LOKIB200_ERR_INVALID : LOKIB200_ERR_CUDA; }
+  static_assert(sizeof(ncclUniqueId) == LOKIB200_COMM_ID_BYTES, "ncclUniqueId size");
+  ncclUniqueId id;
+  const ncclResult_t r = nc->GetUniqueId(&id);
+  if (r != ncclSuccess) { g_create_error = std::string("ncclGetUniqueId: ") + nc->GetErrorString(r); return LOKIB200_ERR_CUDA; }
+  std::memcpy(id128, &id, sizeof(id));
+  return 0;
+}
+
+int lokib200_comm_init_rank(lokib200_engine* h, const void* id128, int32_t rank, int32_t n_ranks) {
+  if (!h || !id128 || n_ranks < 1 || rank < 0 || rank >= n_ranks) return fail(h, LOKIB200_ERR_INVALID, "bad communicator arguments");
+  NcclApi* nc = nccl_api();
+  if (!nc->ok) return fail(h, LOKIB200_ERR_CUDA, nc->why);
+  if (h->comm) return fail(h, LOKIB200_ERR_INVALID, "the engine already has a communicator");
+  CK(cudaSetDevice(h->cfg.device));
+  ncclUniqueId id;
+  std::memcpy(&id, id128, sizeof(id));
+  NK(nc->CommInitRank(&h->comm, n_ranks, id, rank));
+  h->comm_size = n_ranks; h->comm_rank = rank; h->comm_local_group = false;
+  return 0;
+}
+
+int lokib200_comm_init_all(lokib200_engine* const* engines, int32_t n) {
+  if (!engines || n < 1) return LOKIB200_ERR_INVALID;
+  lokib200_engine* h = engines[0];
+  NcclApi* nc = nccl_api();
+  if (!nc->ok) return fail(h, LOKIB200_ERR_CUDA, nc->why);
+  std::vector<int> devs(n);
+  for (int i = 0; i < n; ++i) {
+    if (!engines[i] || engines[i]->comm) return fail(h, LOKIB200_ERR_INVALID, "null engine or engine with a communicator");
+    devs[i] = engines[i]->cfg.device;
+    for (int j = 0; j < i; ++j) if (devs[j] == devs[i]) return fail(h, LOKIB200_ERR_INVALID, "lokib200_comm_init_all needs one engine per device");
+  }
+  std::vector<ncclComm_t> comms(n);
+  NK(nc->CommInitAll(comms.data(), n, devs.data()));
+  for (int i = 0; i < n; ++i) { engines[i]->comm = comms[i]; engines[i]->comm_size = n; engines[i]->comm_rank = i; engines[i]->comm_local_group = n > 1; }
+  return 0;
+}
+
+int lokib200_comm_destroy(lokib200_engine* h) {
+  if (!h) return LOKIB200_ERR_INVALID;
+  if (!h->comm) return 0;
+  NcclApi* nc = nccl_api();
+  CK(cudaSetDevice(h->cfg.device));
+  CK(cudaStreamSynchronize(h->stream));
+  NK(nc->CommDestroy(h->comm));
+  h->comm = nullptr; h->comm_size = 1; h->comm_rank = 0; h->comm_local_group = false;
+  return 0;
+}
+
+int32_t lokib200_comm_size(const lokib200_engine* h) { return h ? h->comm_size : 0; }
+
+int lokib200_comm_allreduce_results(lokib200_engine* const* engines, int32_t n, double* const* d_results) {
+  if (!engines || n < 1 || !engines[0]) return LOKIB200_ERR_INVALID;
+  lokib200_engine* h = engines[0];
+  NcclApi* nc = nccl_api();
+  if (!nc->ok) return fail(h, LOKIB200_ERR_CUDA, nc->why);
+  for (int i = 0; i < n; ++i) if (!engines[i] || !engines[i]->comm || engines[i]->part_len != h->part_len) return fail(h, LOKIB200_ERR_INVALID, "engine without a communicator / different process sets");
+  // one NCCL group: [0, SUM_COUNT) by sum, [SUM_COUNT, HEADER) by max, [HEADER, L) by sum -- in place, on each engine's stream
+  NK(nc->GroupStart());
+  for (int i = 0; i < n; ++i) {
+    lokib200_engine* e = engines[i];
+    double* v = (d_results && d_results[i]) ? d_results[i] : e->d_result;
+    ncclResult_t r = nc->AllReduce(v, v, R_SUM_COUNT, ncclDouble, ncclSum, e->comm, e->stream);
+    if (r == ncclSuccess) r = nc->AllReduce(v + R_SUM_COUNT, v + R_SUM_COUNT, R_HEADER - R_SUM_COUNT, ncclDouble, ncclMax, e->comm, e->stream);
+    if (r == ncclSuccess) r = nc->AllReduce(v + R_HEADER, v + R_HEADER, e->part_len - R_HEADER, ncclDouble, ncclSum, e->comm, e->stream);
+    if (r != ncclSuccess) { nc->GroupEnd(); return fail(h, LOKIB200_ERR_CUDA, std::string("ncclAllReduce: ") + nc->GetErrorString(r)); }
+  }
+  NK(nc->GroupEnd());
+  return 0;
+}
+
+int lokib200_comm_allreduce_histograms(lokib200_engine* const* engines, int32_t n) {
+  if (!engines || n < 1 || !engines[0]) return LOKIB200_ERR_INVALID;
+  lokib200_engine* h = engines[0];
+  NcclApi* nc = nccl_api();
+  if (!nc->ok) return fail(h, LOKIB200_ERR_CUDA, nc->why);
+  for (int i = 0; i < n; ++i) if (!engines[i] || !engines[i]->comm || !engines[i]->hist.enabled) return fail(h, LOKIB200_ERR_INVALID, "engine without a communicator / histogram grid");
+  for (int i = 0; i < n; ++i) {
+    lokib200_engine* e = engines[i];
+    if (!e->d_hist_red) {
+      const HistGrid& g = e->hist;
+      const size_t tot = static_cast<size_t>(g.nEn) * (1 + g.nC + e->cfg.n_phases) + static_cast<size_t>(g.nR) * g.nA;
+      if (cudaSetDevice(e->cfg.device) != cudaSuccess || cudaMalloc(&e->d_hist_red, tot * 8) != cudaSuccess) return fail(h, LOKIB200_ERR_CUDA, "cudaMalloc(histogram reduction buffer)");
+    }
+  }
+  NK(nc->GroupStart());
+  for (int i = 0; i < n; ++i) {
+    lokib200_engine* e = engines[i];
+    const HistGrid& g = e->hist;
+    const size_t ne = g.nEn, nea = ne * g.nC, nev = static_cast<size_t>(g.nR) * g.nA, nep = ne * e->cfg.n_phases;
+    unsigned long long* red = e->d_hist_red;   // the accumulators keep the rank's own counts: reducing twice must not double them
+    ncclResult_t r = nc->AllReduce(e->d_eeh, red, ne, ncclUint64, ncclSum, e->comm, e->stream);
+    if (r == ncclSuccess) r = nc->AllReduce(e->d_eah, red + ne, nea, ncclUint64, ncclSum, e->comm, e->stream);
+    if (r == ncclSuccess) r = nc->AllReduce(e->d_evh, red + ne + nea, nev, ncclUint64, ncclSum, e->comm, e->stream);
+    if (r == ncclSuccess) r = nc->AllReduce(e->d_eeh_per, red + ne + nea + nev, nep, ncclUint64, ncclSum, e->comm, e->stream);
+    if (r != ncclSuccess) { nc->GroupEnd(); return fail(h, LOKIB200_ERR_CUDA, std::string("ncclAllReduce: ") + nc->GetErrorString(r)); }
+    e->hist_reduced = true;
+  }
+  NK(nc->GroupEnd());
+  return 0;
+}
+
+int lokib200_sample_moments_device(lokib200_engine* h) {
   int rc = ensure_ready(h, false);
   if (rc) return rc;
   CK(cudaSetDevice(h->cfg.device));
@@ -696,10 +855,17 @@ int lokib200_sample_moments(lokib200_engine* h, double* result) {
   k_finalize<<<h->part_len, 32, 0, h->stream>>>(h->d_adv_part, h->adv_blocks, nullptr, 0, h->d_smp_part, h->smp_blocks, nullptr, h->P, h->d_result);
   h->launches += 2;
   CK(cudaGetLastError());
-  CK(cudaMemcpyAsync(h->h_result, h->d_result, h->part_len * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-  CK(cudaStreamSynchronize(h->stream));
-  if (result) std::memcpy(result, h->h_result, h->part_len * sizeof(double));
   return 0;
+}
+
+int lokib200_sample_moments(lokib200_engine* h, double* result) {
+  int rc = lokib200_sample_moments_device(h);
+  if (rc) return rc;
+  if (h->comm && !h->comm_local_group) {
+    lokib200_engine* one[1] = {h};
+    if ((rc = lokib200_comm_allreduce_results(one, 1, nullptr))) return rc;
+  }
+  return lokib200_read_result(h, result);
 }
 
 int lokib200_regrid_energy_histograms(lokib200_engine* h, double new_max) {
@@ -708,6 +874,7 @@ int lokib200_regrid_energy_histograms(lokib200_engine* h, double new_max) {
   if (!h->hist.enabled || !(new_max > 0)) return fail(h, LOKIB200_ERR_INVALID, "no histogram grid / bad energy");
   CK(cudaSetDevice(h->cfg.device));
   HistGrid& g = h->hist;
+  h->hist_reduced = false;
   g.e_step = (0.0 + 1 * (new_max - 0.0) / static_cast<double>(g.nEn)) - 0.0;   // BMC.C:1507-1508
   h->max_eedf_energy = new_max;
   const size_t ne = g.nEn;
@@ -723,6 +890,8 @@ int lokib200_set_histogram_grid(lokib200_engine* h, double max_eedf_energy) {
   CK(cudaSetDevice(h->cfg.device));
   const lokib200_config& c = h->cfg;
   HistGrid& g = h->hist;
+  h->hist_reduced = false;
+  if (h->d_hist_red) { cudaFree(h->d_hist_red); h->d_hist_red = nullptr; }
   g.enabled = 1; g.cylindrical = c.is_cylindrically_symmetric; g.nEn = c.n_energy_cells; g.nC = c.n_cos_cells; g.nR = c.n_radial_cells; g.nA = c.n_axial_cells;
   // Eigen::LinSpaced(size, low, high)[1] - [0] with size = cells + 1 (BMC.C:1863-1882)
   g.e_step = (0.0 + 1 * (max_eedf_energy - 0.0) / static_cast<double>(g.nEn)) - 0.0;
@@ -748,6 +917,7 @@ int lokib200_sample_histograms(lokib200_engine* h, int32_t phase_index) {
   if (phase_index >= h->cfg.n_phases) return fail(h, LOKIB200_ERR_INVALID, "phase_index out of range");
   CK(cudaSetDevice(h->cfg.device));
   HistGrid g = h->hist;
+  h->hist_reduced = false;
   g.eeh_phase = (phase_index >= 0) ? h->d_eeh_per + static_cast<size_t>(phase_index) * g.nEn : nullptr;
   k_sample<<<h->smp_blocks, ADV_THREADS, static_cast<size_t>(g.nEn) * 4 + 16, h->stream>>>(h->st, h->cfg.n_electrons, g, h->P, h->d_smp_part);
   ++h->launches;
@@ -759,18 +929,21 @@ int lokib200_fetch_histograms(lokib200_engine* h, double* eeh, double* eah, doub
   if (!h || !h->hist.enabled) return fail(h, LOKIB200_ERR_INVALID, "no histogram grid");
   CK(cudaSetDevice(h->cfg.device));
   const HistGrid& g = h->hist;
-  auto fetch = [&](double* dst, const unsigned long long* src, size_t n) -> int {
-    if (!dst) return 0;
-    std::vector<unsigned long long> tmp(n);
-    CK(cudaMemcpyAsync(tmp.data(), src, n * 8, cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
-    for (size_t i = 0; i < n; ++i) dst[i] = static_cast<double>(tmp[i]);
-    return 0;
-  };
-  int rc;
-  if ((rc = fetch(eeh, h->d_eeh, g.nEn)) || (rc = fetch(eah, h->d_eah, static_cast<size_t>(g.nEn) * g.nC)) ||
-      (rc = fetch(evh, h->d_evh, static_cast<size_t>(g.nR) * g.nA)) || (rc = fetch(eeh_periodic, h->d_eeh_per, static_cast<size_t>(g.nEn) * h->cfg.n_phases)))
-    return rc;
+  const size_t ne = g.nEn, nea = ne * g.nC, nev = static_cast<size_t>(g.nR) * g.nA, nep = ne * h->cfg.n_phases;
+  const bool red = h->hist_reduced && h->d_hist_red;   // after lokib200_comm_allreduce_histograms: the counts of all shards
+  const unsigned long long* src[4] = {red ? h->d_hist_red : h->d_eeh, red ? h->d_hist_red + ne : h->d_eah, red ? h->d_hist_red + ne + nea : h->d_evh,
+                                      red ? h->d_hist_red + ne + nea + nev : h->d_eeh_per};
+  double* dst[4] = {eeh, eah, evh, eeh_periodic};
+  const size_t len[4] = {ne, nea, nev, nep};
+  std::vector<unsigned long long> tmp[4];
+  for (int a = 0; a < 4; ++a) {
+    if (!dst[a]) continue;
+    tmp[a].resize(len[a]);
+    CK(cudaMemcpyAsync(tmp[a].data(), src[a], len[a] * 8, cudaMemcpyDeviceToHost, h->stream));
+  }
+  CK(cudaStreamSynchronize(h->stream));   // one synchronisation for all four arrays
+  for (int a = 0; a < 4; ++a)
+    if (dst[a]) for (size_t i = 0; i < len[a]; ++i) dst[a][i] = static_cast<double>(tmp[a][i]);
   return 0;
 }
 
@@ -780,7 +953,11 @@ int lokib200_step_injected(lokib200_engine* h, int32_t n, const lokib200_electro
   if (rc) return rc;
   if (n <= 0 || !in || !t_sync || !draws || n_draws <= 0 || !out || !ev) return fail(h, LOKIB200_ERR_INVALID, "bad arguments");
   CK(cudaSetDevice(h->cfg.device));
-  ElectronIO *d_in = nullptr, *d_out = nullptr; EventIO* d_ev = nullptr; double *d_ts = nullptr, *d_dr = nullptr;
+  struct Scratch {   // released on every return path
+    ElectronIO *in = nullptr, *out = nullptr; EventIO* ev = nullptr; double *ts = nullptr, *dr = nullptr;
+    ~Scratch() { for (void* q : {static_cast<void*>(in), static_cast<void*>(out), static_cast<void*>(ev), static_cast<void*>(ts), static_cast<void*>(dr)}) if (q) cudaFree(q); }
+  } sc;
+  ElectronIO *&d_in = sc.in, *&d_out = sc.out; EventIO*& d_ev = sc.ev; double *&d_ts = sc.ts, *&d_dr = sc.dr;
   CK(cudaMalloc(&d_in, sizeof(ElectronIO) * n)); CK(cudaMalloc(&d_out, sizeof(ElectronIO) * n)); CK(cudaMalloc(&d_ev, sizeof(EventIO) * n));
   CK(cudaMalloc(&d_ts, sizeof(double) * n)); CK(cudaMalloc(&d_dr, sizeof(double) * static_cast<size_t>(n) * n_draws));
   CK(cudaMemcpyAsync(d_in, in, sizeof(ElectronIO) * n, cudaMemcpyHostToDevice, h->stream));
@@ -803,7 +980,6 @@ int lokib200_step_injected(lokib200_engine* h, int32_t n, const lokib200_electro
   CK(cudaMemcpyAsync(out, d_out, sizeof(ElectronIO) * n, cudaMemcpyDeviceToHost, h->stream));
   CK(cudaMemcpyAsync(ev, d_ev, sizeof(EventIO) * n, cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
-  cudaFree(d_in); cudaFree(d_out); cudaFree(d_ev); cudaFree(d_ts); cudaFree(d_dr);
   return 0;
 }
 

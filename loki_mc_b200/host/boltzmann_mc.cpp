@@ -125,9 +125,17 @@ struct lokib200_job {
   }
   double maxElecEnergyNow = 0;   // electronEnergies.maxCoeff() of the current ensemble (BMC.C:721)
 
-  int advance(double tSync, bool sample) {
-    for (auto* e : engines) { int rc = lokib200_advance_to_sync_device(e, trialCollisionFrequency, tSync, sample ? 1 : 0, nullptr); if (rc) return engineFail(e, rc); }
-    // (the launches above are asynchronous: all GPUs run concurrently; the blocking reads below collect them)
+  // With a communicator (lokib200_comm_init_all for the engines of this process, lokib200_comm_init_rank for one engine per process) the
+  // result vectors are combined on the devices by one grouped NCCL all-reduce per interval and ONE vector is read back; every rank
+  // of a multi-process job then takes identical decisions from identical numbers.  Without one, the engines are read one by one.
+  bool useComm = false;
+  int collect() {
+    if (useComm) {
+      int rc = lokib200_comm_allreduce_results(engines.data(), static_cast<int32_t>(engines.size()), nullptr);
+      if (rc) return engineFail(engines[0], rc);
+      if ((rc = lokib200_read_result(engines[0], res.data()))) return engineFail(engines[0], rc);
+      return 0;
+    }
     for (size_t i = 0; i < engines.size(); ++i) {
       int rc = lokib200_read_result(engines[i], tmp.data());
       if (rc) return engineFail(engines[i], rc);
@@ -135,13 +143,14 @@ struct lokib200_job {
     }
     return 0;
   }
+  int advance(double tSync, bool sample) {
+    // (the launches are asynchronous: all GPUs run concurrently; collect() waits for them)
+    for (auto* e : engines) { int rc = lokib200_advance_to_sync_device(e, trialCollisionFrequency, tSync, sample ? 1 : 0, nullptr); if (rc) return engineFail(e, rc); }
+    return collect();
+  }
   int sampleNow() {
-    for (size_t i = 0; i < engines.size(); ++i) {
-      int rc = lokib200_sample_moments(engines[i], tmp.data());
-      if (rc) return engineFail(engines[i], rc);
-      combine(i == 0);
-    }
-    return 0;
+    for (auto* e : engines) { int rc = lokib200_sample_moments_device(e); if (rc) return engineFail(e, rc); }
+    return collect();
   }
 
   // nonParallelCollisionTasks' accumulations (BMC.C:1303-1328) from the combined result vector
@@ -238,7 +247,12 @@ struct lokib200_job {
     if (eah) std::copy(carryEah.begin(), carryEah.end(), eah);
     if (evh) std::fill(evh, evh + nEv, 0.0);
     if (per) std::copy(carryEehPeriodic.begin(), carryEehPeriodic.end(), per);
+    if (useComm) {   // the counts of all shards, combined on the devices; engine 0 returns them
+      int rc = lokib200_comm_allreduce_histograms(engines.data(), static_cast<int32_t>(engines.size()));
+      if (rc) return engineFail(engines[0], rc);
+    }
     for (auto* e : engines) {
+      if (useComm && e != engines[0]) break;
       int rc = lokib200_fetch_histograms(e, eeh ? a.data() : nullptr, eah ? b.data() : nullptr, evh ? c.data() : nullptr, per ? d.data() : nullptr);
       if (rc) return engineFail(e, rc);
       if (eeh) for (size_t i = 0; i < nE; ++i) eeh[i] += a[i];
@@ -336,7 +350,9 @@ struct lokib200_job {
     trialCollisionFrequency = nuLast;                                                  // :515
     // ---- t = 0 sample (:306-310) ----
     nSamplingPoints = 1; nSynchronizationPoints = 1; collisionCounterAfterSS = 0; nIntegrationPoints = 0; totalIntegratedTime = 0;
-    if ((rc = sampleNow()) || (rc = calculateMeanDataForSwarmParams())) return rc;
+    if ((rc = sampleNow())) return rc;
+    nElectrons = res[LOKIB200_R_N_SAMPLED];   // all shards of all ranks
+    if ((rc = calculateMeanDataForSwarmParams())) return rc;
     const int over = std::max(1, ctl.sync_over_sampling);
     // ---- main loop (:320-384) ----
     while ((!goodStatisticalErrors && ctl.errors_to_be_checked) || static_cast<double>(nIntegrationPoints) < ctl.n_integration_points ||
@@ -416,6 +432,8 @@ int lokib200_job_create(lokib200_engine* const* engines, int32_t n_engines, cons
   j->L = LOKIB200_RESULT_LEN(j->P);
   j->nElectrons = 0;
   for (auto* e : j->engines) { lokib200_config ce; lokib200_get_config(e, &ce); j->nElectrons += static_cast<double>(ce.n_electrons); }
+  j->useComm = lokib200_comm_size(engines[0]) > 1;
+  for (auto* e : j->engines) if ((lokib200_comm_size(e) > 1) != j->useComm) { delete j; return LOKIB200_ERR_INVALID; }
   j->totalGasDensity = j->cfg.gas_density;
   j->relDensities.resize(j->P);
   lokib200_get_rel_densities(engines[0], j->relDensities.data());

@@ -62,6 +62,11 @@ int lokib200_run_setup(const char* input_dir, const char* setup_file, const char
         eng.e.push_back(h);
         if (lokib200_set_processes(h, &soa)) throw lokihost::SetupError(std::string("engine: ") + lokib200_last_error(h));
       }
+      // shards of one job share a communicator: per sampling interval their result vectors are combined by one grouped NCCL all-reduce on the
+      // devices.  Without a usable NCCL the driver reads the engines one by one and adds on the host.
+      if (n_devices > 1 && lokib200_comm_init_all(eng.e.data(), n_devices) != 0 && verbose)
+        std::printf("\033[1;33mPay attention to the following warning:\nno NCCL communicator (%s): the per-interval sums of the %d GPUs are combined on the host\n\033[0m",
+                    lokib200_last_error(eng.e[0]), n_devices);
       const lokib200_solve_controls ctl = in.controls();
       JobHandle jh;
       if (lokib200_job_create(eng.e.data(), n_devices, &ctl, &jh.j)) throw lokihost::SetupError("could not create the job");

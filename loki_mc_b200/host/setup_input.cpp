@@ -1032,7 +1032,8 @@ ProcessSet Mixture::flatten(double gasTemperature) const {   // BMC.C:29-271, :4
       ps.xsOffset.push_back(static_cast<int64_t>(ps.xsEnergy.size()));
       ps.xsEnergy.insert(ps.xsEnergy.end(), e.begin(), e.end()); ps.xsValue.insert(ps.xsValue.end(), v.begin(), v.end());
       ps.descriptions.push_back(c->description()); ps.collisionOf.push_back(c);
-      if (c->type == "momentumConservationIonization" && t != 1) throw SetupError("Trying to assign the angularScatteringType 'momentumConservationIonization' to the process\n" + c->description() + "\nwhich is not 'Ionization'");
+      if (c->angularType == "momentumConservationIonization" && t != 1) throw   // BMC.C:195-198
+        SetupError("Trying to assign the angularScatteringType 'momentumConservationIonization' to the process\n" + c->description() + "\nwhich is not 'Ionization'");
       if (c->isReverse) {   // :209-266
         const State* prod = c->products[0];
         const double Mp = prod->gas->get("mass");

@@ -276,7 +276,7 @@ def test_full_size_energy_balance(name, n):
                                              ("arhe_true", 60.0, 150.0), ("air", 40.0, 100.0), ("ls_att_aniso", 40.0, 100.0),
                                              ("n2_true_acb", 30.0, 60.0)] + [(nm, 5.0, 12.0) for nm in gio.FIELD_GT_MODELS])
 def test_tile_kernel_equals_thread_kernel(name, e_hi, maxE, monkeypatch):
-    """the shared-memory tile kernel (compacted event rounds) and the one-thread-per-electron kernel consume the same per-electron
+    """the shared-memory kernel (streaming pool, production for large ensembles) and the one-thread-per-electron kernel consume the same per-electron
     draw streams, so they must produce the same ensemble bit for bit and the same event counters -- also when electrons are
     born (ionization) or lost (attachment): only the slots touched by the population control at t_sync may differ."""
     import loki_mc_b200 as lk
@@ -286,7 +286,7 @@ def test_tile_kernel_equals_thread_kernel(name, e_hi, maxE, monkeypatch):
     rng = np.random.default_rng(99)
     s0 = _start_state(g, n, rng, 1e-2, e_hi)
     out = {}
-    for kern in ("thread", "tile"):
+    for kern in ("thread", "stream"):
         monkeypatch.setenv("LOKIB200_KERNEL", kern)
         eng = _engine(g, n, seed=4242, first_electron_id=10)
         eng.build_tables(maxE)
@@ -297,6 +297,12 @@ def test_tile_kernel_equals_thread_kernel(name, e_hi, maxE, monkeypatch):
         res += [eng.advance(nu, it / nu, sample=True) for it in range(2, 4)]
         out[kern] = (eng.get_ensemble(), res, first)
         eng.close()
+    for form in ("stream",):
+        _compare_with_thread_kernel(g, n, out["thread"], out[form], R)
+
+
+def _compare_with_thread_kernel(g, n, ref, got, R):
+    out = {"thread": ref, "tile": got}
     P = len(g["p_type"])
     # exact agreement holds until the population control reshuffles slots (its victim draws depend on list order), i.e. for the
     # first interval always, and for all three when nothing is born or lost

@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
         for s in declared:
             assert hasattr(L, s), "missing symbol " + s
         assert sorted(symbols) == declared, header
-    assert L.lokib200_abi_version() == 1
+    assert L.lokib200_abi_version() == 2
 
 
 def test_no_cpu_fallback():
