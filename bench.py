@@ -72,35 +72,6 @@ class ClockSampler(threading.Thread):
         return dict(sm_mhz=float(np.median(self.sm)) if self.sm else None, sm_max_mhz=self.mx, reasons=reasons, samples=len(self.sm))
 
 
-def combine_results(dist, world, src, gathered, out, sum_count, header):
-    """ONE collective per sampling interval: all-gather of the per-GPU result vectors (2.6 KB each), then SUM / MAX locally
-    (include/lokib200.h: entries [SUM_COUNT, HEADER) combine with max, all others with sum).  Leaves the combined vector in `out`."""
-    import torch
-    L = out.numel()
-    if world > 1:
-        dist.all_gather_into_tensor(gathered, src)
-        g2 = gathered.view(world, L)
-        torch.sum(g2, dim=0, out=out)
-        out[sum_count:header] = g2[:, sum_count:header].max(dim=0).values
-    elif src is not out:
-        out.copy_(src)
-    return out
-
-
-def combine_ring(dist, world, ring, gathered, sum_count, header):
-    """Batched form of combine_results for the device-resident loop: `ring` holds the result vectors of K consecutive intervals
-    ([K, L]); ONE all-gather moves all of them (K x 2.6 KB per GPU) and the same SUM / MAX rule is applied per interval.
-    Returns the combined [K, L] tensor."""
-    import torch
-    if world == 1:
-        return ring
-    dist.all_gather_into_tensor(gathered, ring.reshape(-1))
-    g3 = gathered.view(world, ring.shape[0], ring.shape[1])
-    comb = g3.sum(dim=0)
-    comb[:, sum_count:header] = g3[:, :, sum_count:header].max(dim=0).values
-    return comb
-
-
 def measured_hbm_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -177,34 +148,49 @@ def run_reference_arm(args):
     print(json.dumps(line))
 
 
-def run_time_to_3sigma(args):
+def run_time_to_3sigma(which="default", with_reference=True):
     """BASELINE.json's second metric: wall time from job start until the run's own stop criterion is met with every swarm parameter within
-    3 sigma_eff of the reference.  Setup: tests/fixtures/Input/fx/setup_out_dc.in (two gases, anisotropic models, two E/N
-    jobs) at 2e4 electrons, through the setup-file entry point (lokib200_run_setup: parse -> solve -> post-process -> write the output
-    folder).  sigma_eff per parameter = max(reference's reported std, scatter of its 10 replicas, this run's reported std), from
-    tests/golden/ensemble_fixture.json.  Beside it: the unmodified reference on the same setup on the host cores, when oracle/_ref is there."""
+    3 sigma_eff of the reference, through the setup-file entry point (lokib200_run_setup: parse -> solve -> post-process ->
+    write the output folder).
+      which = "default": BASELINE.json configs[0], Code/Input/default_setup.in verbatim with the GUI off (O2, 5 jobs E/N = 1 ... 100 Td, 2e4
+                         electrons, 1e4 integration points); input data = the reference's own Input/ files (copy under oracle/_ref/Input);
+      which = "fixture": tests/fixtures/Input/fx/setup_out_dc.in (two synthetic gases, anisotropic models, two E/N jobs) at 2e4 electrons.
+    sigma_eff per parameter = max(reference's reported std, scatter of its replicas, this run's reported std), from tests/golden/ensemble_*.json.
+    Beside it (with_reference): the unmodified reference on the same setup on the host cores, when oracle/_ref is there."""
     import shutil
     import tempfile
     import loki_mc_b200 as lk
     from oracle import run_reference as rr
-    fix = os.path.join(ROOT, "tests", "fixtures", "Input")
-    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "ensemble_fixture.json")))["jobs"]
-    n = 20000
-    text = open(os.path.join(fix, "fx", "setup_out_dc.in")).read().replace("nElectrons: 400", "nElectrons: %d" % n)
     tmp = tempfile.mkdtemp()
+    if which == "default":
+        gj = json.load(open(os.path.join(ROOT, "tests", "golden", "ensemble_default_setup.json")))
+        gold, text, inp, folder = gj["jobs"], gj["setup_text"], os.path.join(rr.REFDIR, "Input"), "swarm_O2_short"
+        workload = "Code/Input/default_setup.in verbatim (GUI off): O2, 5 jobs E/N = 1, 5, 10, 50, 100 Td, 2e4 electrons, 1e4 integration points [BASELINE.json configs[0]]"
+        if not os.path.isdir(inp):
+            raise RuntimeError("the reference's Input/ data files are not here (oracle/_ref/Input)")
+        key_of = lambda sub: sub
+    else:
+        inp = os.path.join(ROOT, "tests", "fixtures", "Input")
+        gold = json.load(open(os.path.join(ROOT, "tests", "golden", "ensemble_fixture.json")))["jobs"]
+        text = open(os.path.join(inp, "fx", "setup_out_dc.in")).read().replace("nElectrons: 400", "nElectrons: 20000")
+        folder, workload = "fx_dc", "fx/setup_out_dc.in: 2 jobs (E/N = 20, 80 Td), 2e4 electrons, reference stop criterion"
+        key_of = lambda sub: "setup_out_dc/" + sub
     path = os.path.join(tmp, "job.in")
     with open(path, "w") as f:
         f.write(text)
-    lk.run_setup(fix, path, os.path.join(tmp, "warm"), verbose=False)          # untimed: context creation, module load
+    warm = text.replace("nIntegrationPoints: 1E4", "nIntegrationPoints: 500").replace("[1,5,10,50,100]", "[10]")
+    with open(os.path.join(tmp, "warm.in"), "w") as f:
+        f.write(warm)
+    lk.run_setup(inp, os.path.join(tmp, "warm.in"), os.path.join(tmp, "warm"), verbose=False)          # untimed: context creation, module load
     t0 = time.perf_counter()
-    lk.run_setup(fix, path, os.path.join(tmp, "out"), verbose=False)
+    lk.run_setup(inp, path, os.path.join(tmp, "out"), verbose=False)
     wall = time.perf_counter() - t0
     worst, checked, events = 0.0, 0, 0.0
-    for sub in sorted(os.listdir(os.path.join(tmp, "out", "fx_dc"))):
-        d = os.path.join(tmp, "out", "fx_dc", sub)
+    for sub in sorted(os.listdir(os.path.join(tmp, "out", folder))):
+        d = os.path.join(tmp, "out", folder, sub)
         if not os.path.isdir(d):
             continue
-        mine, g = rr.parse_swarm(os.path.join(d, "swarmParameters.txt")), gold["setup_out_dc/" + sub]
+        mine, g = rr.parse_swarm(os.path.join(d, "swarmParameters.txt")), gold[key_of(sub)]
         det = rr.parse_details(os.path.join(d, "MCSimDetails.txt"))
         events += det["total number of real collisions"] + det["total number of null collisions"]
         for key, mean in g["mean"].items():
@@ -213,18 +199,157 @@ def run_time_to_3sigma(args):
             rel = max(g["reported_relstd"].get(key, 0.0), g["std"][key] / abs(mean), mine.get(key + "/relstd", 0.0), 4e-3)
             worst = max(worst, abs(mine[key] - mean) / (rel * abs(mean)))
             checked += 1
-    line = dict(metric="time_to_3sigma_s", value=wall, unit="s", higher_is_better=False, n_gpus=1, data="synthetic fixture gases (tests/fixtures/Input/fx)",
-                config=dict(workload="fx/setup_out_dc.in: 2 jobs (E/N = 20, 80 Td), 2e4 electrons, reference stop criterion", electrons=n),
-                within_3sigma=bool(worst <= 3.0), worst_deviation_sigma=worst, parameters_checked=checked, events=events, events_per_s=events / wall)
-    if rr.available():
-        dst = os.path.join(rr.REFDIR, "Input", "fx")
-        shutil.rmtree(dst, ignore_errors=True)
-        shutil.copytree(os.path.join(fix, "fx"), dst)
-        res = rr.run(text, "fx_dc")
+    line = dict(metric="time_to_3sigma_s", value=wall, unit="s", higher_is_better=False, n_gpus=1, data="reference input files" if which == "default" else "synthetic fixture gases",
+                config=dict(workload=workload), within_3sigma=bool(worst <= 3.0), worst_deviation_sigma=worst, parameters_checked=checked, events=events,
+                events_per_s=events / wall)
+    if which == "default":
+        line["reference_recorded"] = dict(value=float(np.mean(gj["wall"])), unit="s", cores=gj["threads"], kind="reference",
+                                          sample="unmodified lokimc on the same setup, %d replicas in the build container (oracle/gen_default_setup_golden.py)" % len(gj["wall"]))
+    if with_reference and rr.available():
+        if which != "default":
+            dst = os.path.join(rr.REFDIR, "Input", "fx")
+            shutil.rmtree(dst, ignore_errors=True)
+            shutil.copytree(os.path.join(inp, "fx"), dst)
+        res = rr.run(text, folder, timeout=7200)
         line["reference"] = dict(value=res["wall"], unit="s", cores=res["threads"], kind="reference",
-                                 sample="unmodified lokimc (oracle/_ref) on the same setup file and electron count, all host threads")
+                                 sample="unmodified lokimc (oracle/_ref) on the same setup file and electron count, all host threads of this box")
+        line["speedup_vs_reference"] = res["wall"] / wall
     shutil.rmtree(tmp, ignore_errors=True)
-    print(json.dumps(line))
+    return line
+
+
+def build_id():
+    """identifies the CUDA sources a profile was captured from: first 16 hex digits of sha256 over loki_mc_b200/csrc/*"""
+    import hashlib
+    h = hashlib.sha256()
+    src = os.path.join(ROOT, "loki_mc_b200", "csrc")
+    for f in sorted(os.listdir(src)):
+        h.update(open(os.path.join(src, f), "rb").read())
+    return h.hexdigest()[:16]
+
+
+WORKLOADS = {
+    "n2_aniso": "N2 DC E/N=100 Td anisotropic scattering [BASELINE.json configs[1]]",
+    "air": "N2/O2 = 0.8/0.2 DC 100 Td, attachment + ionization + rotational/vibrational levels, P = 151 [BASELINE.json configs[4]]",
+    "arhe": "Ar/He = 0.5/0.5 DC 300 Td, ionization growth (population control) [BASELINE.json configs[2]]",
+    "o2_sdcs": "O2 DC 50 Td (process set of default_setup.in) [BASELINE.json configs[0]]",
+    "reid_dc": "Reid ramp model gas, DC 12 Td",
+}
+
+
+class Arm:
+    """One engine per rank on one explicit torch stream; for world > 1 the shards of the job share a communicator INSIDE the engine
+    (lokib200_comm_init_rank): torch.distributed only carries the 128-byte NCCL id, the barrier and the max-over-ranks of the timings."""
+
+    def __init__(self, torch, dist, lk, model, n, rank, world, local, stream):
+        self.torch, self.dist, self.lk, self.rank, self.world = torch, dist, lk, rank, world
+        self.g = load_model(model)
+        self.model, self.n = model, n
+        self.eng = lk.Engine(self.g, n, seed=0x4C6F4B49, device=local, first_electron_id=rank * n)
+        self.eng.set_stream(stream.cuda_stream)
+        if world > 1:
+            idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+            if rank == 0:
+                idt.copy_(torch.frombuffer(bytearray(lk.comm_unique_id()), dtype=torch.uint8))
+            dist.broadcast(idt, 0)
+            self.eng.comm_init_rank(idt.cpu().numpy().tobytes(), rank, world)
+        self.P, self.L = self.eng.P, lk.result_len(self.eng.P)
+        self.mean_e = MEAN_ENERGY_EV.get(model, 1.0)
+        ratio = self.mean_e / (1.5 * KB_OVER_QE * self.g["cond"]["gas_temperature"])
+        self.mx = self.eng.init_ensemble(ratio)
+        self.eng.build_tables(2.0 * self.mx)
+        self.nu = self.eng.check_nu_trial(self.mx, self.eng.table_info()["nu_max_last"], horizon=11.0)
+        self.t = self.eng.time
+        self.res = None
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def host_step(self, S=1.0, hist=False):
+        """what the product's job driver does per interval (host/boltzmann_mc.cpp): trial-frequency / table check on the host, the blocking
+        C-ABI call -- which for world > 1 ends with the in-engine all-reduce -- and a read of the combined vector from pinned memory"""
+        R = self.lk.R
+        self.nu = self.eng.check_nu_trial(self.mx, self.nu, horizon=S + 10.0)
+        self.t += S / self.nu
+        self.res = self.eng.advance(self.nu, self.t, sample=True)
+        if hist:
+            self.eng.sample_histograms(-1)
+        self.mx = max(self.res[R.MAX_EPS], self.res[R.MAX_EPS_SEEN])
+        return self.res
+
+    def measure(self, steps, warmup, relax, S=1.0, hist=False):
+        torch, R, eng = self.torch, self.lk.R, self.eng
+        for _ in range(relax):
+            self.host_step(S, False)
+        if hist:   # histograms are sampled after the steady state (BoltzmannMC.C:1551-1571): grid of checkSteadyState
+            eng.set_histogram_grid(1.2 * self.mx)
+        for _ in range(warmup):
+            self.host_step(S, hist)
+        mean_energy_now = self.res[R.SUM_EPS] / self.res[R.N_SAMPLED]
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        # ---- leg 1: end to end through the blocking C-ABI call ----
+        self.barrier()
+        ev_e2e = 0.0
+        e0.record()
+        for _ in range(steps):
+            r = self.host_step(S, hist)
+            ev_e2e += r[R.N_REAL] + r[R.N_NULL]
+        e1.record()
+        self.barrier()
+        ms_e2e = e0.elapsed_time(e1)
+        # ---- leg 2: device-resident: per interval the advance, the in-engine all-reduce (world > 1) and, optionally, the histogram pass; the
+        # combined result vectors stay in a device ring; no host round trip and no torch kernel inside the region ----
+        self.nu = eng.check_nu_trial(self.mx, self.nu, horizon=S * steps + 10.0)   # one bound for the whole region
+        ring = torch.zeros(steps, self.L, dtype=torch.float64, device="cuda")
+        eng.kernel_time_ms()
+        launches0 = eng.launch_count()
+        self.barrier()
+        e0.record()
+        for i in range(steps):
+            self.t += S / self.nu
+            ptr = ring[i].data_ptr()
+            eng.advance_device(self.nu, self.t, True, ptr)
+            if self.world > 1:
+                eng.allreduce_results(ptr)
+            if hist:
+                eng.sample_histograms(-1)
+        e1.record()
+        self.barrier()
+        ms_dev = e0.elapsed_time(e1)
+        adv_ms, adv_n = eng.kernel_time_ms()
+        launches = eng.launch_count() - launches0
+        tot = ring.sum(dim=0).cpu().numpy()            # after the all-reduce every row already holds the sum over ranks
+        ev_dev = float(tot[R.N_REAL] + tot[R.N_NULL])
+        if ring[:, R.OVERFLOW].max().item() != 0:
+            raise SystemExit("birth/death list overflow inside the timed region: the event counts are invalid")
+        last = ring[-1].cpu().numpy()
+        self.mx = max(float(ring[:, R.MAX_EPS].max()), float(ring[:, R.MAX_EPS_SEEN].max()))
+        tm = torch.tensor([ms_dev, ms_e2e], dtype=torch.float64, device="cuda")
+        if self.world > 1:
+            self.dist.all_reduce(tm, op=self.dist.ReduceOp.MAX)
+            ev_e2e_all = ev_e2e            # the blocking call returns the combined vector: already the sum over ranks
+        else:
+            ev_e2e_all = ev_e2e
+        ms_dev, ms_e2e = float(tm[0]), float(tm[1])
+        return dict(ms_dev=ms_dev, ms_e2e=ms_e2e, ev_dev=ev_dev, ev_e2e=ev_e2e_all, adv_ms=adv_ms, adv_n=adv_n, launches=launches, mean_energy=float(mean_energy_now),
+                    real_fraction=float(last[R.N_REAL] / (last[R.N_REAL] + last[R.N_NULL])), nu=self.nu, steps=steps,
+                    nu_exceeded=float(tot[R.N_NU_EXCEEDED]), table_clamped=float(tot[R.N_TABLE_CLAMPED]))
+
+    def close(self):
+        self.eng.close()
+
+
+def roofline_of(m, n_per_gpu, world, peak, peak_src, S=1.0):
+    """algorithmic bytes = 128 / S per event (8 FP64 state words in + out once per interval of S mean free times); achieved =
+    bytes of one launch / average duration of the advance kernel (CUDA events on the engine's stream around every launch)"""
+    ev_launch = m["ev_dev"] / world / m["steps"]
+    bpe = STATE_BYTES_PER_EVENT / S
+    achieved = bpe * ev_launch / (m["adv_ms"] * 1e-3) / 1e9 if m["adv_ms"] > 0 else None
+    return dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=(achieved / peak) if achieved else None, kernel="k_advance_stream" if n_per_gpu >= 1_200_000 else "k_advance",
+                kernel_ms=m["adv_ms"], kernel_launches=m["adv_n"], bytes_per_event=bpe, peak_source=peak_src,
+                kernel_share_of_step=m["adv_ms"] * m["steps"] / m["ms_dev"] if m["ms_dev"] > 0 else None)
 
 
 def main():
@@ -236,14 +361,16 @@ def main():
     ap.add_argument("--model", default="n2_aniso")
     ap.add_argument("--electrons", type=float, default=1e7, help="electrons per GPU")
     ap.add_argument("--relax", type=int, default=60, help="untimed relaxation intervals before the warm-up")
-    ap.add_argument("--ref-electrons", type=int, default=200_000)
+    ap.add_argument("--ref-electrons", type=int, default=1_000_000)
     ap.add_argument("--ref-points", type=int, default=500)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--batch", type=int, default=16, help="device leg: intervals whose result vectors share one collective")
-    ap.add_argument("--time-to-3sigma", action="store_true", help="second metric of BASELINE.json: setup file in, swarm parameters out, on one GPU")
+    ap.add_argument("--no-extras", action="store_true", help="only the headline workload (skip the `also` legs and time_to_3sigma)")
+    ap.add_argument("--time-to-3sigma", action="store_true", help="second metric of BASELINE.json alone: setup file in, swarm parameters out, on one GPU")
+    ap.add_argument("--t3s-setup", default="default", choices=["default", "fixture"])
     args = ap.parse_args()
     if args.time_to_3sigma:
-        return run_time_to_3sigma(args)
+        print(json.dumps(run_time_to_3sigma(args.t3s_setup, with_reference=True)))
+        return
     if args.warmup < 3:
         args.warmup = 3
     if args.impl == "reference":
@@ -252,160 +379,89 @@ def main():
     import torch
     import torch.distributed as dist
     import loki_mc_b200 as lk
-    R = lk.R
     rank, world, local = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback")
     torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # NCCL's version / debug lines must not land on stdout next to the JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    g = load_model(args.model)
-    n = int(args.electrons)
-    eng = lk.Engine(g, n, seed=0x4C6F4B49, device=local, first_electron_id=rank * n)
-    # everything (engine kernels, NCCL all-reduces, timing events) runs on ONE explicit non-default torch stream
+    # everything (engine kernels, in-engine NCCL all-reduces, timing events) runs on ONE explicit non-default torch stream
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
     assert stream.cuda_stream != 0
-    eng.set_stream(stream.cuda_stream)
-    P, L = eng.P, lk.result_len(eng.P)
-    mean_e = MEAN_ENERGY_EV.get(args.model, 1.0)
-    ratio = mean_e / (1.5 * KB_OVER_QE * g["cond"]["gas_temperature"])
-    mx = eng.init_ensemble(ratio)
-    eng.build_tables(2.0 * mx)
-    nu = eng.check_nu_trial(mx, eng.table_info()["nu_max_last"], horizon=11.0)
+    n = int(args.electrons)
+    peak, peak_src = measured_hbm_peak()
 
-    d_res = torch.zeros(L, dtype=torch.float64, device="cuda")
-    d_buf = [torch.zeros(L, dtype=torch.float64, device="cuda") for _ in range(2)]
-    d_gather = torch.zeros(world * L, dtype=torch.float64, device="cuda")
-    d_events = torch.zeros(1, dtype=torch.float64, device="cuda")
-    comm_stream = torch.cuda.Stream()
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def combine(src):
-        return combine_results(dist, world, src, d_gather, d_res, R.SUM_COUNT, R.HEADER)
-
-    def host_step(t):
-        """the blocking C-ABI call with the host-side trial-frequency logic a driver runs every interval"""
-        nonlocal nu, mx
-        nu = eng.check_nu_trial(mx, nu, horizon=11.0)
-        t += 1.0 / nu
-        if world > 1:   # the result vector stays on the device until the ranks have combined it: one collective, one device -> host read per interval
-            eng.advance_device(nu, t, True, d_buf[0].data_ptr()); combine(d_buf[0]); res = d_res.cpu().numpy()
-        else:
-            res = eng.advance(nu, t, sample=True)
-        mx = max(res[R.MAX_EPS], res[R.MAX_EPS_SEEN])
-        return t, res
-
-    # ---- relaxation + warm-up (untimed) ----
-    t = eng.time
-    for _ in range(args.relax + args.warmup):
-        t, res = host_step(t)
-    mean_energy_now = res[R.SUM_EPS] / res[R.N_SAMPLED]
-
-    # ---- timed leg 1: e2e through the blocking C-ABI call ----
+    arm = Arm(torch, dist, lk, args.model, n, rank, world, local, stream)
     sampler = ClockSampler(local); sampler.start()
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev_e2e = 0.0
-    e0.record()
-    for _ in range(args.steps):
-        t, res = host_step(t)
-        ev_e2e += res[R.N_REAL] + res[R.N_NULL]
-    e1.record()
-    barrier()
-    ms_e2e = e0.elapsed_time(e1)
-
-    # ---- timed leg 2: device-resident (no host round trip inside the region) ----
-    nu = eng.check_nu_trial(mx, nu, horizon=float(args.steps) + 11.0)   # one bound for the whole region
-    eng.kernel_time_ms()                                                 # reset the per-kernel event log
-    launches0 = eng.launch_count()
-    d_events.zero_()
-    K = max(1, min(args.batch, args.steps))               # intervals per collective (result vectors wait in a device ring)
-    rings = [torch.zeros(K, L, dtype=torch.float64, device="cuda") for _ in range(2)]
-    d_gather_ring = torch.zeros(world * K * L, dtype=torch.float64, device="cuda")
-    with torch.cuda.stream(comm_stream):                 # untimed: first use of the combine kernels (module load) and of the collective
-        comb = combine_ring(dist, world, rings[0], d_gather_ring, R.SUM_COUNT, R.HEADER)
-        d_events.add_(comb[:, R.N_REAL].sum() + comb[:, R.N_NULL].sum())
-        d_res.copy_(comb[0])
-    comm_stream.synchronize()
-    d_events.zero_()
-    barrier()
-    e0.record()
-    free_evt = [None, None]
-    for i in range(args.steps):
-        t += 1.0 / nu
-        slot, which = i % K, (i // K) & 1
-        ring = rings[which]
-        if slot == 0 and free_evt[which] is not None:
-            stream.wait_event(free_evt[which])          # the collective that read this ring two batches ago is done
-        eng.advance_device(nu, t, True, ring[slot].data_ptr())
-        if slot == K - 1 or i == args.steps - 1:
-            ready = torch.cuda.Event(); ready.record(stream)
-            with torch.cuda.stream(comm_stream):        # one collective per K intervals, on a side stream
-                comm_stream.wait_event(ready)
-                comb = combine_ring(dist, world, ring, d_gather_ring, R.SUM_COUNT, R.HEADER)[:slot + 1]
-                d_events.add_(comb[:, R.N_REAL].sum() + comb[:, R.N_NULL].sum())
-                d_res.copy_(comb[slot])
-                free_evt[which] = torch.cuda.Event(); free_evt[which].record(comm_stream)
-    stream.wait_stream(comm_stream)
-    e1.record()
-    barrier()
-    ms_dev = e0.elapsed_time(e1)
+    m = arm.measure(args.steps, args.warmup, args.relax)
     clocks = sampler.stop()
-    adv_ms, adv_n = eng.kernel_time_ms()
-    fp64_peak = eng.measure_fp64_peak() if rank == 0 else None
-    launches = eng.launch_count() - launches0
-    ev_dev = float(d_events.item())   # already the sum over ranks when world > 1
+    fp64_peak = arm.eng.measure_fp64_peak() if rank == 0 else None
+    P, L, nE = arm.P, arm.L, arm.eng.table_info()["nE"]
+    arm.close()
 
-    tm = torch.tensor([ms_dev, ms_e2e], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-    ms_dev, ms_e2e = float(tm[0]), float(tm[1])
-    final = d_res.cpu().numpy()
+    also = []
+    if not args.no_extras:
+        # more of what BASELINE.json names, each a short leg of the same measurement (same rules: warm-up >= 3, inputs >> L2, CUDA events)
+        extra = [dict(tag="configs[1] with histograms every sample (post-steady-state cadence, BoltzmannMC.C:1551-1571)", model=args.model, n=n, S=1.0, hist=True, steps=20),
+                 dict(tag="configs[1] at synchronizationTimeXMaxCollisionFrequency = 10 (Headers/BoltzmannMC.h:72)", model=args.model, n=n, S=10.0, hist=False, steps=10),
+                 dict(tag="configs[4] air, 1e9 electrons over 8 GPUs = 1.25e8 per GPU", model="air", n=125_000_000, S=1.0, hist=False, steps=10),
+                 dict(tag="configs[2] Ar/He ionization growth, 1e8 electrons over 8 GPUs = 1.25e7 per GPU", model="arhe", n=12_500_000, S=1.0, hist=False, steps=20),
+                 dict(tag="reference-size ensemble (1e5 electrons, configs[0] process set)", model="o2_sdcs", n=100_000, S=1.0, hist=False, steps=100)]
+        for x in extra:
+            a2 = Arm(torch, dist, lk, x["model"], x["n"], rank, world, local, stream)
+            mm = a2.measure(x["steps"], 3, 40 if x["n"] <= 12_500_000 else 25, S=x["S"], hist=x["hist"])
+            a2.close()
+            if rank == 0:
+                rf = roofline_of(mm, x["n"], world, peak, peak_src, S=x["S"])
+                also.append(dict(workload=x["tag"], process_set=x["model"], electrons_per_gpu=x["n"], sync_factor=x["S"], histograms=x["hist"], steps=x["steps"],
+                                 value=mm["ev_dev"] / (mm["ms_dev"] * 1e-3), unit="events/s", ms_per_step=mm["ms_dev"] / x["steps"],
+                                 e2e=mm["ev_e2e"] / (mm["ms_e2e"] * 1e-3), kernel_ms=mm["adv_ms"], hbm_fraction=rf["frac"], real_fraction=mm["real_fraction"],
+                                 mean_energy_eV=mm["mean_energy"]))
     if rank == 0:
-        peak, peak_src = measured_hbm_peak()
         traffic, fp64 = None, None
-        try:   # DRAM bytes and FP64 operations of one K1 launch from the committed ncu captures (same workload only)
-            tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
-            if tj["electrons"] == n and args.model == "n2_aniso":
+        try:   # DRAM bytes and FP64 operations of one K1 launch from an ncu capture of THESE sources (tools/capture_traffic.py); stale captures are ignored
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))
+            if tj["electrons"] == n and tj["model"] == args.model and tj["build"] == build_id():
                 traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
-                # second ceiling of SURVEY.md 8(d): FP64 pipe.  flop per event from ncu's SASS counters (DFMA = 2), peak = DFMA chain measured live
-                flop_per_event = tj["fp64_flop"] / tj["events"]
-                fp64 = dict(flop_per_event=flop_per_event, peak=fp64_peak, unit="TFLOP/s", peak_source="measured live (lokib200_measure_fp64_peak: 16 DFMA chains per thread)")
+                fp64 = dict(flop_per_event=tj["fp64_flop"] / tj["events"], peak=fp64_peak, unit="TFLOP/s",
+                            peak_source="measured live (lokib200_measure_fp64_peak: 16 DFMA chains per thread)")
         except Exception:
             pass
-        ev_per_launch_rank = ev_dev / world / args.steps
-        achieved = STATE_BYTES_PER_EVENT * ev_per_launch_rank / (adv_ms * 1e-3) / 1e9 if adv_ms > 0 else None
+        rf = roofline_of(m, n, world, peak, peak_src)
+        rf["traffic"] = traffic
+        ev_per_launch_rank = m["ev_dev"] / world / args.steps
         line = dict(
-            metric="collision_events_per_sec", value=ev_dev / (ms_dev * 1e-3), unit="events/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
-            ms_per_step=ms_dev / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64", data="synthetic",
-            config=dict(workload="N2 DC E/N=100 Td anisotropic scattering, 1e7 electrons per GPU, reference cadence (sync factor 1, ensemble sums every interval) [BASELINE.json configs[1]]",
+            metric="collision_events_per_sec", value=m["ev_dev"] / (m["ms_dev"] * 1e-3), unit="events/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
+            ms_per_step=m["ms_dev"] / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64", data="synthetic",
+            config=dict(workload=WORKLOADS.get(args.model, args.model) + ", %.3g electrons per GPU, reference cadence (sync factor 1, ensemble sums and one combine of the shards every interval)" % n,
                         process_set=args.model, electrons_per_gpu=n, processes=P, sync_factor=1.0, relax_intervals=args.relax,
-                        mean_energy_eV=mean_energy_now, nu_trial=nu, table_mib=round(eng.table_info()["nE"] * ((P + 15) // 16 * 16) * 8 * 3 / 2 ** 20, 1),   # cumulative table (8 B / entry) + its row-pair form (16 B / entry)
-                        l2_policy="state 640 MB per GPU >> 126 MB L2: every step streams it from HBM", intervals_per_collective=K, real_fraction=float(final[R.N_REAL] / (final[R.N_REAL] + final[R.N_NULL]))),
-            e2e=dict(value=ev_e2e / (ms_e2e * 1e-3), unit="events/s", h2d_bytes_per_step=16 * world,
-                     d2h_bytes_per_step=8 * L * world, ms_per_step=ms_e2e / args.steps),
-            gpu_launches=int(launches * world), clocks=clocks,
-            roofline=dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=(achieved / peak) if achieved else None, traffic=traffic,
-                          kernel="k_advance", kernel_ms=adv_ms, kernel_launches=adv_n, bytes_per_event=STATE_BYTES_PER_EVENT, peak_source=peak_src,
-                          kernel_share_of_step=adv_ms * args.steps / ms_dev if ms_dev > 0 else None))   # (the engine times at most its first 256 launches per leg)
-        if fp64 is not None and adv_ms > 0:
-            fp64["achieved"] = fp64["flop_per_event"] * ev_per_launch_rank / (adv_ms * 1e-3) / 1e12
+                        mean_energy_eV=m["mean_energy"], nu_trial=m["nu"], table_mib=round(nE * ((P + 15) // 16 * 16) * 8 * 3 / 2 ** 20, 1),   # cumulative table (8 B / entry) + its row-pair form (16 B / entry)
+                        l2_policy="state %.0f MB per GPU >> 126 MB L2: every step streams it from HBM" % (n * 72 / 1e6), collective="in-engine grouped ncclAllReduce per interval" if world > 1 else "none (one GPU)",
+                        real_fraction=m["real_fraction"], nu_exceeded=m["nu_exceeded"], table_clamped=m["table_clamped"]),
+            e2e=dict(value=m["ev_e2e"] / (m["ms_e2e"] * 1e-3), unit="events/s", h2d_bytes_per_step=16 * world, d2h_bytes_per_step=8 * L * world, ms_per_step=m["ms_e2e"] / args.steps),
+            gpu_launches=int(m["launches"] * world), clocks=clocks, roofline=rf)
+        if fp64 is not None and m["adv_ms"] > 0:
+            fp64["achieved"] = fp64["flop_per_event"] * ev_per_launch_rank / (m["adv_ms"] * 1e-3) / 1e12
             fp64["frac"] = fp64["achieved"] / fp64["peak"]
             line["roofline"]["fp64"] = fp64
+        if also:
+            line["also"] = also
         if world == 1 and not args.no_cpu_baseline:
             try:
-                line["cpu_baseline"] = cpu_baseline_port(args.model, mean_e)
+                line["cpu_baseline"] = cpu_baseline_port(args.model, arm.mean_e)
             except Exception as ex:   # the baseline is reported, never required for the GPU number
                 line["cpu_baseline"] = dict(value=None, unit="events/s", cores=os.cpu_count(), kind="port", sample="failed: %s" % ex)
+        if world == 1 and not args.no_extras:
+            try:   # BASELINE.json's second metric on configs[0], Code/Input/default_setup.in verbatim
+                line["time_to_3sigma"] = run_time_to_3sigma("default", with_reference=False)
+            except Exception as ex:
+                line["time_to_3sigma"] = dict(value=None, error=str(ex))
         print(json.dumps(line))
-    eng.close()
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 
