@@ -72,6 +72,16 @@ class ClockSampler(threading.Thread):
         return dict(sm_mhz=float(np.median(self.sm)) if self.sm else None, sm_max_mhz=self.mx, reasons=reasons, samples=len(self.sm))
 
 
+def allreduce_rule(dist, vec, sum_count, header):
+    """CPU mirror of lokib200_comm_allreduce_results (csrc/lokib200.cu) for the gloo tests of the N > 1 host logic: entries [0, SUM_COUNT) and
+    [HEADER, L) of the per-shard result vectors combine by SUM, entries [SUM_COUNT, HEADER) by MAX; three all-reduces in place, as the engine
+    issues them in one NCCL group."""
+    dist.all_reduce(vec[:sum_count], op=dist.ReduceOp.SUM)
+    dist.all_reduce(vec[sum_count:header], op=dist.ReduceOp.MAX)
+    dist.all_reduce(vec[header:], op=dist.ReduceOp.SUM)
+    return vec
+
+
 def measured_hbm_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -148,6 +158,19 @@ def run_reference_arm(args):
     print(json.dumps(line))
 
 
+class StdoutToStderr:
+    """the C++ front end prints warnings and status with printf: keep them off this process's stdout, which carries the JSON line"""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+
+    def __exit__(self, *exc):
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+
+
 def run_time_to_3sigma(which="default", with_reference=True):
     """BASELINE.json's second metric: wall time from job start until the run's own stop criterion is met with every swarm parameter within
     3 sigma_eff of the reference, through the setup-file entry point (lokib200_run_setup: parse -> solve -> post-process ->
@@ -181,10 +204,11 @@ def run_time_to_3sigma(which="default", with_reference=True):
     warm = text.replace("nIntegrationPoints: 1E4", "nIntegrationPoints: 500").replace("[1,5,10,50,100]", "[10]")
     with open(os.path.join(tmp, "warm.in"), "w") as f:
         f.write(warm)
-    lk.run_setup(inp, os.path.join(tmp, "warm.in"), os.path.join(tmp, "warm"), verbose=False)          # untimed: context creation, module load
-    t0 = time.perf_counter()
-    lk.run_setup(inp, path, os.path.join(tmp, "out"), verbose=False)
-    wall = time.perf_counter() - t0
+    with StdoutToStderr():
+        lk.run_setup(inp, os.path.join(tmp, "warm.in"), os.path.join(tmp, "warm"), verbose=False)          # untimed: context creation, module load
+        t0 = time.perf_counter()
+        lk.run_setup(inp, path, os.path.join(tmp, "out"), verbose=False)
+        wall = time.perf_counter() - t0
     worst, checked, events = 0.0, 0, 0.0
     for sub in sorted(os.listdir(os.path.join(tmp, "out", folder))):
         d = os.path.join(tmp, "out", folder, sub)
@@ -334,7 +358,7 @@ class Arm:
             ev_e2e_all = ev_e2e
         ms_dev, ms_e2e = float(tm[0]), float(tm[1])
         return dict(ms_dev=ms_dev, ms_e2e=ms_e2e, ev_dev=ev_dev, ev_e2e=ev_e2e_all, adv_ms=adv_ms, adv_n=adv_n, launches=launches, mean_energy=float(mean_energy_now),
-                    real_fraction=float(last[R.N_REAL] / (last[R.N_REAL] + last[R.N_NULL])), nu=self.nu, steps=steps,
+                    real_fraction=float(last[R.N_REAL] / (last[R.N_REAL] + last[R.N_NULL])), nu=self.nu, steps=steps, kernel=eng.kernel_form(),
                     nu_exceeded=float(tot[R.N_NU_EXCEEDED]), table_clamped=float(tot[R.N_TABLE_CLAMPED]))
 
     def close(self):
@@ -347,7 +371,7 @@ def roofline_of(m, n_per_gpu, world, peak, peak_src, S=1.0):
     ev_launch = m["ev_dev"] / world / m["steps"]
     bpe = STATE_BYTES_PER_EVENT / S
     achieved = bpe * ev_launch / (m["adv_ms"] * 1e-3) / 1e9 if m["adv_ms"] > 0 else None
-    return dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=(achieved / peak) if achieved else None, kernel="k_advance_stream" if n_per_gpu >= 1_200_000 else "k_advance",
+    return dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=(achieved / peak) if achieved else None, kernel=m["kernel"],
                 kernel_ms=m["adv_ms"], kernel_launches=m["adv_n"], bytes_per_event=bpe, peak_source=peak_src,
                 kernel_share_of_step=m["adv_ms"] * m["steps"] / m["ms_dev"] if m["ms_dev"] > 0 else None)
 

@@ -223,6 +223,11 @@ int lokib200_regrid_energy_histograms(lokib200_engine* h, double new_max_eedf_en
 double lokib200_max_accel_energy(const lokib200_engine* h, double initial_energy, double dt);
 /* checkMaxCollisionFrequency (BMC.C:716-763): may rebuild tables; returns the (possibly raised) trial frequency through *nu_trial */
 int lokib200_check_nu_trial(lokib200_engine* h, double max_energy, double horizon, double energy_max_elastic, double* nu_trial);
+/* which form of the advance kernel this engine launches: 0 = one electron per thread (k_advance, small ensembles), 1 = streaming pool in
+ * shared memory (k_advance_stream, large ensembles); the choice is made in lokib200_set_processes from n_electrons and the SM count */
+int32_t lokib200_kernel_form(const lokib200_engine* h);
+/* nominal HBM bandwidth of the engine's device [GB/s] from its memory clock and bus width (status display: fraction of the roofline) */
+double lokib200_device_hbm_gbs(const lokib200_engine* h);
 /* number of kernels launched by this engine so far (bench.py's gpu_launches) */
 int64_t lokib200_launch_count(const lokib200_engine* h);
 /* average device time [ms] of the advance kernel over the launches since the last call (CUDA events on the engine's stream) */
@@ -252,6 +257,9 @@ typedef struct lokib200_solve_controls {   /* numericsMC keys, BMC.h:262-365 (va
   double initial_temp_ratio;             /* initialElecTempOverGasTemp */
   double energy_max_elastic;             /* energyMaxElastic (BMC.C:158) */
   int64_t max_intervals;                 /* safety stop (0 = none); not a reference key */
+  int32_t status_display;                /* gui.terminalDisp contains MCStatus (BMC.h:368-374): print the status table of dispInfo (BMC.C:1895-1948) */
+  int32_t fast_mode;                     /* 0 = the reference's single trial collision frequency (default); 1 = per-energy-band trial frequencies (numericsMC.fastMode, not a reference key) */
+  double status_values[4];               /* header of the status table: E/N [Td], excitation frequency [Hz], field angle [degrees], B/N [Hx] */
 } lokib200_solve_controls;
 
 typedef struct lokib200_solve_results {   /* the public members the reference's sinks read (Output.h:123-147, 794-820) */
@@ -265,6 +273,9 @@ typedef struct lokib200_solve_results {   /* the public members the reference's 
   double total_collisions, null_collisions, collisions_at_ss, null_collisions_at_ss;
   int64_t n_sampling_points, n_integration_points, n_sync_points, n_table_rebuilds;
   int32_t good_statistical_errors, stopped_by_max_collisions;
+  double n_nu_exceeded;     /* collisions that found nu_tot(eps) above the trial frequency they were drawn with (LOKIB200_R_N_NU_EXCEEDED, whole job): the driver raises the trial frequency when it sees one (BMC.C:758-761) */
+  double n_table_clamped;   /* collisions beyond the last table row (LOKIB200_R_N_TABLE_CLAMPED, whole job): the driver rebuilds the tables */
+  double events_per_second; /* (real + null collisions) / elapsed_seconds */
 } lokib200_solve_results;
 
 typedef struct lokib200_job lokib200_job;

@@ -100,7 +100,8 @@ class SolveControls(C.Structure):
                 ("rel_err_mean_energy", C.c_double), ("rel_err_flux_drift", C.c_double), ("rel_err_flux_diff", C.c_double),
                 ("rel_err_bulk_drift", C.c_double), ("rel_err_bulk_diff", C.c_double), ("rel_err_power_balance", C.c_double),
                 ("min_collisions_before_ss", C.c_double), ("max_collisions_before_ss", C.c_double), ("max_collisions_after_ss", C.c_double),
-                ("sync_factor", C.c_double), ("initial_temp_ratio", C.c_double), ("energy_max_elastic", C.c_double), ("max_intervals", C.c_int64)]
+                ("sync_factor", C.c_double), ("initial_temp_ratio", C.c_double), ("energy_max_elastic", C.c_double), ("max_intervals", C.c_int64),
+                ("status_display", C.c_int32), ("fast_mode", C.c_int32), ("status_values", C.c_double * 4)]
 
 
 class SolveResults(C.Structure):
@@ -114,7 +115,8 @@ class SolveResults(C.Structure):
                 ("trial_collision_frequency", C.c_double), ("max_eedf_energy", C.c_double), ("elapsed_seconds", C.c_double),
                 ("total_collisions", C.c_double), ("null_collisions", C.c_double), ("collisions_at_ss", C.c_double), ("null_collisions_at_ss", C.c_double),
                 ("n_sampling_points", C.c_int64), ("n_integration_points", C.c_int64), ("n_sync_points", C.c_int64), ("n_table_rebuilds", C.c_int64),
-                ("good_statistical_errors", C.c_int32), ("stopped_by_max_collisions", C.c_int32)]
+                ("good_statistical_errors", C.c_int32), ("stopped_by_max_collisions", C.c_int32),
+                ("n_nu_exceeded", C.c_double), ("n_table_clamped", C.c_double), ("events_per_second", C.c_double)]
 
 
 class JobData(C.Structure):
@@ -147,7 +149,7 @@ SYMBOLS = ["lokib200_abi_version", "lokib200_device_count", "lokib200_create", "
            "lokib200_job_process_outputs", "lokib200_job_time_series", "lokib200_job_histograms", "lokib200_job_periodic",
            "lokib200_job_periodic_diffusion", "lokib200_job_conditions", "lokib200_job_evdf_max_speed", "lokib200_job_last_error", "lokib200_job_destroy",
            "lokib200_sample_moments_device", "lokib200_comm_unique_id", "lokib200_comm_init_rank", "lokib200_comm_init_all", "lokib200_comm_destroy",
-           "lokib200_comm_size", "lokib200_comm_allreduce_results", "lokib200_comm_allreduce_histograms"]
+           "lokib200_comm_size", "lokib200_comm_allreduce_results", "lokib200_comm_allreduce_histograms", "lokib200_kernel_form", "lokib200_device_hbm_gbs"]
 # every symbol include/lokib200_host.h declares
 HOST_SYMBOLS = ["lokib200_setup_load", "lokib200_setup_destroy", "lokib200_setup_last_error", "lokib200_setup_job_count", "lokib200_setup_job_value",
                 "lokib200_setup_variable_condition", "lokib200_setup_processes", "lokib200_setup_config", "lokib200_setup_controls",
@@ -191,6 +193,8 @@ def lib():
     L.lokib200_max_accel_energy.argtypes = [vp, C.c_double, C.c_double]; L.lokib200_max_accel_energy.restype = C.c_double
     L.lokib200_check_nu_trial.argtypes = [vp, C.c_double, C.c_double, C.c_double, c_dp]
     L.lokib200_launch_count.argtypes = [vp]; L.lokib200_launch_count.restype = C.c_int64
+    L.lokib200_kernel_form.argtypes = [vp]; L.lokib200_kernel_form.restype = C.c_int32
+    L.lokib200_device_hbm_gbs.argtypes = [vp]; L.lokib200_device_hbm_gbs.restype = C.c_double
     L.lokib200_kernel_time_ms.argtypes = [vp, c_dp, c_lp]
     L.lokib200_measure_fp64_peak.argtypes = [vp, c_dp]
     L.lokib200_sample_moments.argtypes = [vp, c_dp]
@@ -438,6 +442,10 @@ class Engine:
     def launch_count(self):
         return int(self.L.lokib200_launch_count(self.h))
 
+    def kernel_form(self):
+        """'k_advance' (one electron per thread) or 'k_advance_stream' (streaming pool): the advance kernel this engine launches"""
+        return "k_advance_stream" if self.L.lokib200_kernel_form(self.h) == 1 else "k_advance"
+
     def kernel_time_ms(self):
         ms = C.c_double(); n = C.c_int64()
         self._check(self.L.lokib200_kernel_time_ms(self.h, C.byref(ms), C.byref(n)))
@@ -487,6 +495,7 @@ class Job:
         c.sync_over_sampling = int(kw.get("sync_over_sampling", 1)); c.sync_factor = float(sync_factor)
         c.initial_temp_ratio = float(initial_temp_ratio); c.energy_max_elastic = float(self.engines[0].energy_max_elastic)
         c.max_intervals = int(max_intervals)
+        c.status_display = int(kw.get("status_display", 0)); c.fast_mode = int(kw.get("fast_mode", 0))
         for k in ("rel_err_mean_energy", "rel_err_flux_drift", "rel_err_flux_diff", "rel_err_bulk_drift", "rel_err_bulk_diff", "rel_err_power_balance"):
             if k in kw:
                 setattr(c, k, float(kw[k])); c.errors_to_be_checked = 1

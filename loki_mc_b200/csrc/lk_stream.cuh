@@ -26,6 +26,10 @@
 namespace lk {
 
 constexpr int POOL = 1024;                       // electrons resident per CTA
+// Every per-slot array has PSTRIDE entries: slot POOL is a DUMMY that nobody ever writes after the kernel's prologue.  Lanes of the flight
+// phase that have no electron read it (their results are discarded), so no lane ever reads a slot that another warp may be writing:
+// compute-sanitizer racecheck is clean without predicated loads (tools/sanitize_stream.py).
+constexpr int PSTRIDE = POOL + 8;
 constexpr int STREAM_THREADS = 256;
 constexpr int STREAM_WARPS = STREAM_THREADS / 32;
 static_assert(POOL == 4 * STREAM_THREADS, "the scan reads the 4 flags of a thread as one 32-bit word");
@@ -43,15 +47,15 @@ constexpr double TALLY_SCALE = 68719476736.0;
 // register as the plain base for the per-thread sums in the ECR and AC+B instantiations (found with compute-sanitizer racecheck; the
 // thread-vs-stream test catches it as a wrong field gain) -- with constant offsets there is only one base to keep.
 struct Tally { unsigned long long gain, loss; unsigned int cnt, pad; };   // fixed point 2^-36 eV, see TALLY_SCALE
-constexpr size_t SM_COL = 0;                                                   // [SC_COLS][POOL] doubles
-constexpr size_t SM_HDR = SM_COL + static_cast<size_t>(SC_COLS) * POOL * 8;    // [R_HEADER] doubles: result header of the CTA
+constexpr size_t SM_COL = 0;                                                   // [SC_COLS][PSTRIDE] doubles
+constexpr size_t SM_HDR = SM_COL + static_cast<size_t>(SC_COLS) * PSTRIDE * 8;    // [R_HEADER] doubles: result header of the CTA
 constexpr size_t SM_GF = SM_HDR + static_cast<size_t>(R_HEADER) * 8;           // [STREAM_THREADS] doubles: per-thread field-gain sums
 constexpr size_t SM_TMAX = SM_GF + static_cast<size_t>(STREAM_THREADS) * 8;    // [2][STREAM_THREADS] doubles: per-thread energy maxima
 constexpr size_t SM_SCAN = SM_TMAX + static_cast<size_t>(STREAM_THREADS) * 16; // [16] u64: warp totals of the scan, range start, flight count
-constexpr size_t SM_USED = SM_SCAN + 16 * 8;                                   // [POOL] u32: draw counters
-constexpr size_t SM_LISTS = SM_USED + static_cast<size_t>(POOL) * 4;           // 4 x [POOL] u16
-constexpr size_t SM_FLAG = SM_LISTS + static_cast<size_t>(POOL) * 2 * 4;       // [POOL] u8
-constexpr size_t SM_MISC = SM_FLAG + POOL;                                     // [8] u32: rare-event counters
+constexpr size_t SM_USED = SM_SCAN + 16 * 8;                                   // [PSTRIDE] u32: draw counters
+constexpr size_t SM_LISTS = SM_USED + static_cast<size_t>(PSTRIDE) * 4;        // 4 x [POOL] u16
+constexpr size_t SM_FLAG = SM_LISTS + static_cast<size_t>(POOL) * 2 * 4;       // [PSTRIDE] u8
+constexpr size_t SM_MISC = SM_FLAG + PSTRIDE;                                  // [8] u32: rare-event counters
 constexpr size_t SM_RS = SM_MISC + 32;                                         // [16] i32: CTA-uniform round state
 // The first NU_STAGE_ROWS rows of nu_tot (the null test of every event interpolates two of them; they are the rows nearly every electron
 // is in) are staged here when the tally records still fit behind them; otherwise the tally starts at SM_NU and the kernel reads nu_tot from
@@ -174,6 +178,8 @@ __global__ void __launch_bounds__(STREAM_THREADS, 2) k_advance_stream(const Mode
   if (tid < MC_COUNT) s_misc[tid] = 0;
   for (int j = tid; j < static_cast<int>(a.pad); j += STREAM_THREADS) reinterpret_cast<double*>(smem_raw + SM_NU)[j] = __ldg(&m.nu_tot[j]);
   reinterpret_cast<unsigned int*>(flag)[tid] = 0u;   // all slots FL_EMPTY
+  if (tid < SC_COLS) col[tid * PSTRIDE + POOL] = 0.0;   // the dummy slot (never written again)
+  if (tid == 0) { s_used[POOL] = 0u; flag[POOL] = FL_EMPTY; }
 
   // the CTA's range [lo, lo + len) of the ensemble; cursors are CTA-uniform offsets into it.  Column c of the state is sid.s.x + lo + c * a.n.
   if (tid == 0) {
@@ -264,10 +270,10 @@ __global__ void __launch_bounds__(STREAM_THREADS, 2) k_advance_stream(const Mode
           const int sl = static_cast<int>(e & 0x7FFFu);
           if (r < nRet) {
             double* const gp = g0 + (out_off + r);
-            const double vx = col[SC_VX * POOL + sl], vy = col[SC_VY * POOL + sl], vz = col[SC_VZ * POOL + sl];
+            const double vx = col[SC_VX * PSTRIDE + sl], vy = col[SC_VY * PSTRIDE + sl], vz = col[SC_VZ * PSTRIDE + sl];
 #pragma unroll
-            for (int c = 0; c < 8; ++c) __stcs(gp + c * a.n, col[c * POOL + sl]);
-            gid[out_off + r] = static_cast<unsigned long long>(__double_as_longlong(col[SC_ID * POOL + sl]));
+            for (int c = 0; c < 8; ++c) __stcs(gp + c * a.n, col[c * PSTRIDE + sl]);
+            gid[out_off + r] = static_cast<unsigned long long>(__double_as_longlong(col[SC_ID * PSTRIDE + sl]));
             if (e & 0x8000u) {                                         // attached: population control refills this position at t_sync
               const long long pos = lo + out_off + r;
               const unsigned int idx = atomicAdd(&L.counters[C_DEAD], 1u);
@@ -277,9 +283,9 @@ __global__ void __launch_bounds__(STREAM_THREADS, 2) k_advance_stream(const Mode
           if (r < nRefill) {
             const double* const gq = g0 + (in_off + r);
 #pragma unroll
-            for (int c = 0; c < 8; ++c) cp_async8(&col[c * POOL + sl], gq + c * a.n);
-            cp_async8(&col[SC_ID * POOL + sl], &gid[in_off + r]);
-            col[SC_T * POOL + sl] = a.t0; s_used[sl] = 0;
+            for (int c = 0; c < 8; ++c) cp_async8(&col[c * PSTRIDE + sl], gq + c * a.n);
+            cp_async8(&col[SC_ID * PSTRIDE + sl], &gid[in_off + r]);
+            col[SC_T * PSTRIDE + sl] = a.t0; s_used[sl] = 0;
           }
         }
         s_tmax[tid] = fmax(s_tmax[tid], eps_end);
@@ -309,19 +315,19 @@ __global__ void __launch_bounds__(STREAM_THREADS, 2) k_advance_stream(const Mode
         if (k < nB) {
           const int sl = listR[k];
           Particle p;
-          p.x = col[SC_X * POOL + sl]; p.y = col[SC_Y * POOL + sl]; p.z = col[SC_Z * POOL + sl];
-          p.vx = col[SC_VX * POOL + sl]; p.vy = col[SC_VY * POOL + sl]; p.vz = col[SC_VZ * POOL + sl];
-          p.nue = col[SC_NUE * POOL + sl]; p.t = col[SC_T * POOL + sl]; p.tcf = NON_DEF;
+          p.x = col[SC_X * PSTRIDE + sl]; p.y = col[SC_Y * PSTRIDE + sl]; p.z = col[SC_Z * PSTRIDE + sl];
+          p.vx = col[SC_VX * PSTRIDE + sl]; p.vy = col[SC_VY * PSTRIDE + sl]; p.vz = col[SC_VZ * PSTRIDE + sl];
+          p.nue = col[SC_NUE * PSTRIDE + sl]; p.t = col[SC_T * PSTRIDE + sl]; p.tcf = NON_DEF;
           p.eps = kinetic_eV(p.vx, p.vy, p.vz);
           PhiloxRng rng;
-          const unsigned long long id = static_cast<unsigned long long>(__double_as_longlong(col[SC_ID * POOL + sl]));
+          const unsigned long long id = static_cast<unsigned long long>(__double_as_longlong(col[SC_ID * PSTRIDE + sl]));
           rng.k0 = static_cast<uint32_t>(a.seed); rng.k1 = static_cast<uint32_t>(a.seed >> 32);
           rng.c0 = static_cast<uint32_t>(id); rng.c1 = static_cast<uint32_t>(id >> 32); rng.c2 = a.interval;
           rng.used = s_used[sl]; rng.blk = 0xFFFFFFFFu;
           EventOut o; o.table_clamped = 0; o.nu_exceeded = 0; o.dE = 0;
           double Vx = 0, Vy = 0, Vz = 0;
           if (GT != GT_FALSE && (GT == GT_TRUE || k >= nBcr)) chosen = thermal_select(m, p, rng, o, Vx, Vy, Vz);
-          else chosen = cold_select(m, p, col[SC_TCF * POOL + sl]);
+          else chosen = cold_select(m, p, col[SC_TCF * PSTRIDE + sl]);
           if (chosen != NULL_COLLISION) chosen = collide_dynamics<GT>(m, chosen, p, Vx, Vy, Vz, rng, o);
           if (o.table_clamped) atomicAdd(&s_misc[MC_CLAMP], 1u);
             if (o.nu_exceeded) atomicAdd(&s_misc[MC_NUEX], 1u);
@@ -336,8 +342,8 @@ __global__ void __launch_bounds__(STREAM_THREADS, 2) k_advance_stream(const Mode
             } else if (type == T_ATTACHMENT) { atomicAdd(&s_misc[MC_ATT], 1u); outcome = FL_DEAD; }
           }                                                        // aborted picks count as null collisions (BMC.C:1137-1140): see s_scan[9]
           seen = p.eps;
-          col[SC_VX * POOL + sl] = p.vx; col[SC_VY * POOL + sl] = p.vy; col[SC_VZ * POOL + sl] = p.vz;
-          col[SC_TCF * POOL + sl] = NON_DEF;                       // the next free time is drawn at the start of the flight (same stream position)
+          col[SC_VX * PSTRIDE + sl] = p.vx; col[SC_VY * PSTRIDE + sl] = p.vy; col[SC_VZ * PSTRIDE + sl] = p.vz;
+          col[SC_TCF * PSTRIDE + sl] = NON_DEF;                       // the next free time is drawn at the start of the flight (same stream position)
           s_used[sl] = rng.used;
           flag[sl] = outcome;
         }
@@ -373,17 +379,17 @@ __global__ void __launch_bounds__(STREAM_THREADS, 2) k_advance_stream(const Mode
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
           Flyer& f = e[j];
-          int sl = 0; bool act = false;
+          int sl = POOL; bool act = false;   // no electron: the dummy slot
           const int item = 2 * it + j;
           if (item < nK) { const int k = 32 * (warp + 8 * item) + lane; if (k < nB) { sl = listR[k]; act = true; } }
           else if (item < nA) { const int k = 32 * (wrot + 8 * (item - nK)) + lane; if (k < nFlr) { sl = listF[k]; act = true; } }
           else if (item < nItems) { const int r = 32 * (warp + 8 * (item - nA)) + lane; if (r < nRefr) { sl = (r < nRetr) ? (listO[r] & 0x7FFF) : listE[r - nRetr]; act = true; } }
           f.sl = sl;
           f.active = act && (flag[sl] == FL_FLIGHT);                // (an electron attached in (3) stays FL_DEAD and retires in the next scan)
-          f.p.x = col[SC_X * POOL + sl]; f.p.y = col[SC_Y * POOL + sl]; f.p.z = col[SC_Z * POOL + sl];
-          f.p.vx = col[SC_VX * POOL + sl]; f.p.vy = col[SC_VY * POOL + sl]; f.p.vz = col[SC_VZ * POOL + sl];
-          f.p.tcf = col[SC_TCF * POOL + sl]; f.p.nue = col[SC_NUE * POOL + sl]; f.p.t = col[SC_T * POOL + sl];
-          f.id = static_cast<unsigned long long>(__double_as_longlong(col[SC_ID * POOL + sl]));
+          f.p.x = col[SC_X * PSTRIDE + sl]; f.p.y = col[SC_Y * PSTRIDE + sl]; f.p.z = col[SC_Z * PSTRIDE + sl];
+          f.p.vx = col[SC_VX * PSTRIDE + sl]; f.p.vy = col[SC_VY * PSTRIDE + sl]; f.p.vz = col[SC_VZ * PSTRIDE + sl];
+          f.p.tcf = col[SC_TCF * PSTRIDE + sl]; f.p.nue = col[SC_NUE * PSTRIDE + sl]; f.p.t = col[SC_T * PSTRIDE + sl];
+          f.id = static_cast<unsigned long long>(__double_as_longlong(col[SC_ID * PSTRIDE + sl]));
           f.used = s_used[sl];
           f.need = f.active && (f.p.tcf == NON_DEF);
           if (f.need) f.used = (f.used + 1u) & ~1u;                 // free-time draws start on an even index (PhiloxRng::align)
@@ -435,9 +441,9 @@ __global__ void __launch_bounds__(STREAM_THREADS, 2) k_advance_stream(const Mode
           if (f.active) {
             const int sl = f.sl;
             gain_round += f.gain;
-            col[SC_X * POOL + sl] = f.p.x; col[SC_Y * POOL + sl] = f.p.y; col[SC_Z * POOL + sl] = f.p.z;
-            col[SC_VX * POOL + sl] = f.p.vx; col[SC_VY * POOL + sl] = f.p.vy; col[SC_VZ * POOL + sl] = f.p.vz;
-            col[SC_TCF * POOL + sl] = f.p.tcf; col[SC_NUE * POOL + sl] = f.p.nue; col[SC_T * POOL + sl] = f.p.t;
+            col[SC_X * PSTRIDE + sl] = f.p.x; col[SC_Y * PSTRIDE + sl] = f.p.y; col[SC_Z * PSTRIDE + sl] = f.p.z;
+            col[SC_VX * PSTRIDE + sl] = f.p.vx; col[SC_VY * PSTRIDE + sl] = f.p.vy; col[SC_VZ * PSTRIDE + sl] = f.p.vz;
+            col[SC_TCF * PSTRIDE + sl] = f.p.tcf; col[SC_NUE * PSTRIDE + sl] = f.p.nue; col[SC_T * PSTRIDE + sl] = f.p.t;
             s_used[sl] = f.used;
             flag[sl] = f.outcome;
           }

@@ -1028,6 +1028,13 @@ int lokib200_check_nu_trial(lokib200_engine* h, double max_energy_now, double ho
   return 0;
 }
 
+double lokib200_device_hbm_gbs(const lokib200_engine* h) {
+  if (!h) return 0.0;
+  int clock_khz = 0, bus_bits = 0;
+  if (cudaDeviceGetAttribute(&clock_khz, cudaDevAttrMemoryClockRate, h->cfg.device) != cudaSuccess || cudaDeviceGetAttribute(&bus_bits, cudaDevAttrGlobalMemoryBusWidth, h->cfg.device) != cudaSuccess) return 0.0;
+  return 2.0 * static_cast<double>(clock_khz) * 1e3 * (bus_bits / 8.0) / 1e9;   // double data rate
+}
+int32_t lokib200_kernel_form(const lokib200_engine* h) { return (h && h->have_processes && h->use_tile) ? 1 : 0; }
 int64_t lokib200_launch_count(const lokib200_engine* h) { return h ? h->launches : 0; }
 
 int lokib200_kernel_time_ms(lokib200_engine* h, double* advance_ms, int64_t* launches) {

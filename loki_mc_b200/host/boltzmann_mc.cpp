@@ -10,6 +10,7 @@
 #include <array>
 #include <chrono>
 #include <cmath>
+#include <cstdio>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -89,6 +90,10 @@ struct lokib200_job {
   std::vector<double> carryEeh, carryEah, carryEehPeriodic;
   double elapsed = 0;
   std::vector<double> res, tmp;
+  double nuExceededTotal = 0, tableClampedTotal = 0;
+  std::chrono::high_resolution_clock::time_point solveStart;
+  bool firstStatus = true;
+  int64_t nPointsBetweenStatErrorsCheck = 128;
 
   int fail(const std::string& m, int code = LOKIB200_ERR_INVALID) { err = m; return code; }
   int engineFail(lokib200_engine* e, int rc) { err = std::string("engine: ") + lokib200_last_error(e); return rc; }
@@ -330,9 +335,46 @@ struct lokib200_job {
       goodStatisticalErrors = true;
   }
 
+  // dispInfo (BMC.C:1895-1948): the reference's status table, plus two lines of the engine's own (events per second and the fraction of the
+  // device's nominal HBM bandwidth that 128 bytes per event at this rate amount to)
+  void dispInfo() {
+    if (firstStatus) { firstStatus = false; std::printf("\n*********Simulation status*********\n\n"); }
+    else { std::printf(" \n"); for (int i = 0; i < 32; ++i) std::printf("\033[1A\033[2K"); }
+    std::printf("E/N: %g Td\nexcitFreq: %g Hz\nE-field angle: %g degrees\nB/N: %g Hx\n\n", ctl.status_values[0], ctl.status_values[1], ctl.status_values[2], ctl.status_values[3]);
+    std::printf("Number of real collisions: %g\nNumber of null collisions: %g\n\n", totalCollisionCounter, nullCollisionCounter);
+    const double secs = std::chrono::duration<double>(std::chrono::high_resolution_clock::now() - solveStart).count();
+    const double rate = secs > 0 ? (totalCollisionCounter + nullCollisionCounter) / secs : 0.0;
+    const double hbm = lokib200_device_hbm_gbs(engines[0]) * static_cast<double>(engines.size());
+    std::printf("Collision events per second: %.4g\nHBM roofline fraction (128 B per event at sync factor %g): %.3f\n\n", rate, ctl.sync_factor,
+                hbm > 0 ? rate * 128.0 / ctl.sync_factor / (hbm * 1e9) : 0.0);
+    std::printf("Current time: %g s\n", time);
+    int blank = 18;
+    if (steadyStateTime == NON_DEF) { std::printf("Mean energy: %g\n", meanEnergies.empty() ? 0.0 : meanEnergies.back()); blank = 19; }
+    else {
+      std::printf("Steady-state time: %g s\n\n", steadyStateTime);
+      if (nIntegrationPoints >= 3 * nPointsBetweenStatErrorsCheck && averagedMeanEnergy != NON_DEF) {
+        blank = 0;
+        const auto& fv = averagedFluxDriftVelocity; const auto& fe = averagedFluxDriftVelocityError;
+        const auto& bv = averagedBulkDriftVelocity; const auto& be = averagedBulkDriftVelocityError;
+        const auto& fD = averagedFluxDiffusionCoeffs; const auto& fE = averagedFluxDiffusionCoeffsError;
+        const auto& bD = averagedBulkDiffusionCoeffs; const auto& bE = averagedBulkDiffusionCoeffsError;
+        std::printf("Number of integration points: %g\n\nMean energy [eV]: %g\nRelative error: %g\n\n", static_cast<double>(nIntegrationPoints), averagedMeanEnergy,
+                    averagedMeanEnergyError / averagedMeanEnergy);
+        std::printf("Flux drift velocity [m/s]: %g %g %g\nRelative error: %g %g %g\n\n", fv[0], fv[1], fv[2], fe[0] / std::fabs(fv[0]), fe[1] / std::fabs(fv[1]), fe[2] / std::fabs(fv[2]));
+        std::printf("Bulk drift velocity [m/s]: %g %g %g\nRelative error: %g %g %g\n\n", bv[0], bv[1], bv[2], be[0] / std::fabs(bv[0]), be[1] / std::fabs(bv[1]), be[2] / std::fabs(bv[2]));
+        std::printf("Flux diffusion coefficients [m^2 s^-1]: %g %g %g\nRelative error: %g %g %g\n\n", fD[0], fD[4], fD[8], fE[0] / fD[0], fE[4] / fD[4], fE[8] / fD[8]);
+        std::printf("Bulk diffusion coefficients [m^2 s^-1]: %g %g %g\nRelative error: %g %g %g\n\n", bD[0], bD[4], bD[8], bE[0] / bD[0], bE[4] / bD[4], bE[8] / bD[8]);
+        std::printf("Power balance relative error: %g\n", powerBalanceRelError);
+      }
+    }
+    for (int i = 0; i < blank; ++i) std::printf("\n");
+    std::fflush(stdout);
+  }
+
   // evaluateEEDF (BMC.C:299-426)
   int evaluateEEDF() {
     const auto start = std::chrono::high_resolution_clock::now();
+    solveStart = start;
     // ---- evaluateNonConstantVariables (BMC.C:428-559) ----
     time = 0; steadyStateTime = NON_DEF;
     double maxInit = 0;
@@ -353,6 +395,7 @@ struct lokib200_job {
     if ((rc = sampleNow())) return rc;
     nElectrons = res[LOKIB200_R_N_SAMPLED];   // all shards of all ranks
     if ((rc = calculateMeanDataForSwarmParams())) return rc;
+    if (ctl.status_display) dispInfo();                                                // :313-315
     const int over = std::max(1, ctl.sync_over_sampling);
     // ---- main loop (:320-384) ----
     while ((!goodStatisticalErrors && ctl.errors_to_be_checked) || static_cast<double>(nIntegrationPoints) < ctl.n_integration_points ||
@@ -369,6 +412,14 @@ struct lokib200_job {
       time = nextSynchronizTime;
       accumulateTallies();
       maxElecEnergyNow = std::max(res[LOKIB200_R_MAX_EPS], res[LOKIB200_R_MAX_EPS_SEEN]);
+      // The reference re-checks the trial frequency before every micro-pass (BMC.C:634); here one bound serves a whole interval, and these two
+      // counters are what tells that it was not enough: some electron met nu_tot(eps) above its trial frequency, or an energy beyond the
+      // tables.  A few stragglers are normal while the ensemble heats up (an electron keeps the frequency its free time was drawn with until
+      // its next event, also in the reference: BMC.C:650-655); more than one event in a thousand means the bound itself failed: raise the
+      // frequency as checkMaxCollisionFrequency does (:758-761) / let the next check rebuild the tables from the energy seen.
+      nuExceededTotal += res[LOKIB200_R_N_NU_EXCEEDED]; tableClampedTotal += res[LOKIB200_R_N_TABLE_CLAMPED];
+      if (res[LOKIB200_R_N_NU_EXCEEDED] > 1e-3 * (res[LOKIB200_R_N_REAL] + res[LOKIB200_R_N_NULL])) trialCollisionFrequency *= 1.1;
+      if (res[LOKIB200_R_N_TABLE_CLAMPED] > 0) { double top = 0; lokib200_table_info(engines[0], nullptr, nullptr, &top, nullptr); maxElecEnergyNow = std::max(maxElecEnergyNow, top); }
       if (!sample) continue;
       ++nSamplingPoints;                                                               // :334-341
       if ((rc = calculateMeanDataForSwarmParams())) return rc;
@@ -384,8 +435,9 @@ struct lokib200_job {
         if ((rc = checkSteadyState())) return rc;                                      // :363-365
       }
       const int dec2 = static_cast<int>(std::fmax(std::log(static_cast<double>(std::max<int64_t>(nIntegrationPoints, 1))) / std::log(2.0) - 9, 7));
-      const int64_t nPointsBetweenStatErrorsCheck = static_cast<int64_t>(std::pow(2, dec2));    // :369-370
+      nPointsBetweenStatErrorsCheck = static_cast<int64_t>(std::pow(2, dec2));                  // :369-370
       if (steadyStateTime != NON_DEF && nIntegrationPoints > 200 && nIntegrationPoints % nPointsBetweenStatErrorsCheck == 0) checkStatisticalErrors();
+      if (ctl.status_display && nSamplingPoints % nPointsBetweenSteadyStateCheck == 0) dispInfo();   // :377-381
     }
     // ---- time averages (:387-396) ----
     totalIntegratedTime = time - steadyStateTime;
@@ -406,6 +458,7 @@ struct lokib200_job {
       }
     }
     checkStatisticalErrors();                                                          // :418
+    if (ctl.status_display) dispInfo();                                                // :421-423
     elapsed = std::chrono::duration<double>(std::chrono::high_resolution_clock::now() - start).count();
     return 0;
   }
@@ -472,6 +525,8 @@ static void fillResults(const lokib200_job* j, lokib200_solve_results* r) {
     r->n_sampling_points = j->nSamplingPoints; r->n_integration_points = j->nIntegrationPoints; r->n_sync_points = j->nSynchronizationPoints;
     r->n_table_rebuilds = j->nTableRebuilds;
     r->good_statistical_errors = j->goodStatisticalErrors; r->stopped_by_max_collisions = j->stoppedByMaxCollisions;
+    r->n_nu_exceeded = j->nuExceededTotal; r->n_table_clamped = j->tableClampedTotal;
+    r->events_per_second = j->elapsed > 0 ? (j->totalCollisionCounter + j->nullCollisionCounter) / j->elapsed : 0.0;
   }
 }
 

@@ -67,11 +67,21 @@ int lokib200_run_setup(const char* input_dir, const char* setup_file, const char
       if (n_devices > 1 && lokib200_comm_init_all(eng.e.data(), n_devices) != 0 && verbose)
         std::printf("\033[1;33mPay attention to the following warning:\nno NCCL communicator (%s): the per-interval sums of the %d GPUs are combined on the host\n\033[0m",
                     lokib200_last_error(eng.e[0]), n_devices);
-      const lokib200_solve_controls ctl = in.controls();
+      lokib200_solve_controls ctl = in.controls();
+      if (!verbose) ctl.status_display = 0;
+      {   // header of the status table (BMC.C:1914-1917): the working conditions of this job
+        auto pick = [&](const std::vector<double>& a, const char* name) { return a[(in.wc.variableCondition == name) ? static_cast<size_t>(job) : 0]; };
+        ctl.status_values[0] = pick(in.wc.reducedElecFieldArray, "reducedElecField"); ctl.status_values[1] = pick(in.wc.excitationFrequencyArray, "excitationFrequency");
+        ctl.status_values[2] = pick(in.wc.elecFieldAngleArray, "elecFieldAngle"); ctl.status_values[3] = pick(in.wc.reducedMagFieldArray, "reducedMagField");
+      }
       JobHandle jh;
       if (lokib200_job_create(eng.e.data(), n_devices, &ctl, &jh.j)) throw lokihost::SetupError("could not create the job");
       lokib200_solve_results res;
       if (lokib200_job_solve(jh.j, &res)) throw lokihost::SetupError(lokib200_job_last_error(jh.j));
+      if (res.n_nu_exceeded > 1e-4 * (res.total_collisions + res.null_collisions) || res.n_table_clamped > 0)
+        std::printf("\033[1;33mPay attention to the following warning:\n%g collisions met a total collision frequency above their trial frequency and %g an energy beyond the "
+                    "cross-section tables inside a synchronisation interval (of %g events); the trial frequency was raised / the tables were rebuilt for the following intervals. "
+                    "[%s = %g]\n\033[0m", res.n_nu_exceeded, res.n_table_clamped, res.total_collisions + res.null_collisions, in.wc.variableCondition.c_str(), in.jobValue(job));
       if (res.stopped_by_max_collisions)   // BMC.C:398-415
         std::printf("\033[1;33mPay attention to the following warning:\nMonte Carlo simulation ended after reaching ''maxCollisionsAfterSteadyState'' indicated in the setup file. "
                     "[%s = %g]\n\033[0m", in.wc.variableCondition.c_str(), in.jobValue(job));
@@ -99,9 +109,9 @@ int lokib200_run_setup(const char* input_dir, const char* setup_file, const char
       lokihost::Report rep(in, job, std::move(d));
       out.write(rep);
       if (verbose)
-        std::printf("job %d/%d  %s = %g : mean energy %.6e eV (rel. err %.2e), %lld integration points, %.3e collisions, power balance %.2e, %.2f s\n", job + 1, in.nJobs(),
+        std::printf("job %d/%d  %s = %g : mean energy %.6e eV (rel. err %.2e), %lld integration points, %.3e collisions, power balance %.2e, %.2f s, %.3e events/s\n", job + 1, in.nJobs(),
                     in.wc.variableCondition.c_str(), in.jobValue(job), res.averaged_mean_energy, res.averaged_mean_energy_error / res.averaged_mean_energy,
-                    static_cast<long long>(res.n_integration_points), res.total_collisions, res.power_balance_rel_error, res.elapsed_seconds);
+                    static_cast<long long>(res.n_integration_points), res.total_collisions, res.power_balance_rel_error, res.elapsed_seconds, res.events_per_second);
       if (summary) {
         summary->n_jobs = job + 1; summary->last_mean_energy = res.averaged_mean_energy; summary->total_collisions += res.total_collisions + res.null_collisions;
         summary->device_seconds += res.elapsed_seconds;

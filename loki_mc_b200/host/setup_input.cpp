@@ -1235,6 +1235,10 @@ lokib200_solve_controls SetupInput::controls() const {   // BMC.h:291-365
   s.sync_over_sampling = has("synchronizationOverSampling") ? static_cast<int32_t>(num("synchronizationOverSampling")) : 1;
   s.initial_temp_ratio = has("initialElecTempOverGasTemp") ? num("initialElecTempOverGasTemp") : 0.01;
   s.energy_max_elastic = processes.energyMaxElastic;
+  s.fast_mode = has("fastMode") ? (tree->value("electronKinetics.numericsMC.fastMode") == "true" ? 1 : 0) : 0;   // not a reference key: default = reference behaviour
+  const std::string gui = tree->has("gui.isOn") ? tree->value("gui.isOn") : "false";
+  if (gui == "true" || gui == "True" || gui == "1")
+    for (const auto& o : tree->childNames("gui.terminalDisp")) if (o == "MCStatus") s.status_display = 1;   // BMC.h:368-374
   return s;
 }
 

@@ -1,4 +1,5 @@
-"""N > 1 host-side logic on CPU (gloo, world_size 2): the result-vector combine bench.py uses per sampling interval, and the
+"""N > 1 host-side logic on CPU (gloo, world_size 2): the rule by which the shards' result vectors combine per sampling interval (what
+lokib200_comm_allreduce_results does over NCCL inside the engine: three all-reduces, SUM / MAX / SUM), and the
 sharding of an ensemble by global electron id.  The CPU oracle stands in for the engine (it defines the same draw streams), so
 these tests pin the property the multi-GPU path relies on: shards keyed by global electron id reproduce the single-process
 trajectories, integer-valued outputs add up exactly and the ensemble sums agree to rounding."""
@@ -16,7 +17,7 @@ import golden_io as gio
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-SUM_COUNT, HEADER = 34, 36
+SUM_COUNT, HEADER = 34, 37   # LOKIB200_R_SUM_COUNT, LOKIB200_R_HEADER
 
 
 def _worker(rank, world, port, name, n, q):
@@ -34,9 +35,7 @@ def _worker(rank, world, port, name, n, q):
     s0 = np.vstack([rng.normal(size=(3, n)) * 1e-3, d * np.sqrt(2 * eps * gio.QE / gio.ME), np.full((1, n), -123456789.0), np.zeros((1, n))])
     lo_i, hi_i = rank * n // world, (rank + 1) * n // world
     ens = lo.Ensemble(m, hi_i - lo_i, 77, lo_i); ens.set(s0[:, lo_i:hi_i])
-    gathered = torch.zeros(world * L, dtype=torch.float64); out = torch.zeros(L, dtype=torch.float64)
     total = None
-    ring_rows, combined_rows = [], []
     for it in range(1, 4):
         r = ens.advance(nu, it / nu, it, population_control=0)
         st = ens.get(); mom_n = st.shape[1]
@@ -46,13 +45,11 @@ def _worker(rank, world, port, name, n, q):
         vec[6] = e.sum(); vec[7:10] = st[0:3].sum(1); vec[10:13] = st[3:6].sum(1); vec[31] = mom_n
         vec[34] = e.max()
         vec[HEADER:HEADER + P] = r["counts"]; vec[HEADER + P:HEADER + 2 * P] = r["gain"]; vec[HEADER + 2 * P:] = r["loss"]
-        bench.combine_results(dist, world, torch.from_numpy(vec), gathered, out, SUM_COUNT, HEADER)
+        vec[36] = 1.0 if (rank == 1 and it == 2) else 0.0       # an overflow flag raised on one rank must reach every rank (MAX entry)
+        out = bench.allreduce_rule(dist, torch.from_numpy(vec), SUM_COUNT, HEADER)
+        assert out[36] == (1.0 if it == 2 else 0.0)
+        out[36] = 0.0
         total = out.clone() if total is None else total + out
-        ring_rows.append(torch.from_numpy(vec.copy())); combined_rows.append(out.clone())
-    # the batched form used by the device-resident loop: one all-gather for all three intervals gives the same vectors
-    ring = torch.stack(ring_rows)
-    comb = bench.combine_ring(dist, world, ring, torch.zeros(world * ring.numel(), dtype=torch.float64), SUM_COUNT, HEADER)
-    assert torch.equal(comb, torch.stack(combined_rows))
     if rank == 0:
         q.put((total.numpy(), out.numpy()))
     full = np.zeros((8, n))
