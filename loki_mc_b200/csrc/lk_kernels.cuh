@@ -48,7 +48,17 @@ struct HistGrid {             // grids of BMC.C:1862-1883; steps computed on the
   int enabled, cylindrical, nEn, nC, nR, nA, phase, pad;
   double e_step, c_first, c_step, r_step, a_first, a_step;
   unsigned long long *eeh, *eah, *evh, *eeh_phase;   // eeh_phase already points at the row of the current phase (or null)
+  // shared-memory tiles of the two 2-D grids (k_sample): energy rows [0, ea_rows) x all cos cells, radial rows [0, ev_rows) x axial cells
+  // [ev_a0, ev_a0 + ev_aw): where the bulk of a swarm lives.  0 rows = no tile (every count goes to global memory).
+  int ea_rows, ev_rows, ev_a0, ev_aw;
+  double inv_e, inv_c, inv_r, inv_a;   // reciprocals of the four steps (fast path of hist_bin)
 };
+
+// 16-bit counters, two per 32-bit word: a CTA flushes its tiles before any counter can reach 2^16 (HIST_PASS electrons per pass)
+constexpr long long HIST_PASS = 65280;
+__host__ __device__ inline size_t hist_tile_words(const HistGrid& h) {
+  return (static_cast<size_t>(h.ea_rows) * h.nC + 1) / 2 + (static_cast<size_t>(h.ev_rows) * h.ev_aw + 1) / 2;
+}
 
 struct AdvArgs {
   long long n;
@@ -98,27 +108,67 @@ __device__ __forceinline__ void sample_moments(bool alive, double x, double y, d
   }
 }
 
-// histogramCount / histogram2DCount (Math.C:61-81, :106-127) for one electron
-__device__ __forceinline__ void sample_histograms(const HistGrid& h, double vx, double vy, double vz, double eps, unsigned int* s_eeh) {
-  const int ie = static_cast<int>((eps - 0.0) / h.e_step);
+// histogramCount / histogram2DCount (Math.C:61-81, :106-127) for one electron.  The EEDF row is privatised per CTA (s_eeh); the two 2-D grids
+// are privatised where the swarm is dense (s_ea, s_ev: 16-bit counters packed in pairs, native 32-bit shared atomics) and counted straight
+// in global memory elsewhere.  One 64-bit global atomic per electron and grid -- the first form of this pass -- serialised on the few
+// hundred bins that hold most of the swarm: 0.38 ms for 1e7 electrons against 0.08 ms for reading them (profiles/r2_hist_*).
+// bin index static_cast<int>((value - first) / step) as the reference computes it (Math.C:72, :118-119), without the FP64 division on the
+// common path: (value - first) * (1 / step) differs from the quotient by a few ulp, so whenever it is not within 1e-7 of an integer both
+// truncate to the same bin; otherwise (one value in ten million) the division decides.  Bit-exact, four divisions fewer per electron.
+__device__ __forceinline__ int hist_bin(double value, double first, double step, double inv_step) {
+  const double d = value - first, t = d * inv_step;
+  if (fabs(t - rint(t)) < 1e-7) return static_cast<int>(d / step);
+  return static_cast<int>(t);
+}
+
+__device__ __forceinline__ void sample_histograms(const HistGrid& h, double vx, double vy, double vz, double eps, unsigned int* s_eeh, unsigned int* s_ea, unsigned int* s_ev) {
+  const int ie = hist_bin(eps, 0.0, h.e_step, h.inv_e);
   if (ie < h.nEn) atomicAdd(&s_eeh[ie], 1u);
   if (h.cylindrical) {
-    const double cosang = vz / sqrt((vx * vx + vy * vy) + vz * vz);
-    const int ic = static_cast<int>((cosang - h.c_first) / h.c_step);
-    if (ie < h.nEn && ie >= 0 && ic < h.nC && ic >= 0) atomicAdd(&h.eah[static_cast<size_t>(ie) * h.nC + ic], 1ull);
-    const double vr = sqrt(vx * vx + vy * vy);
-    const int ir = static_cast<int>((vr - 0.0) / h.r_step), ia = static_cast<int>((vz - h.a_first) / h.a_step);
-    if (ir < h.nR && ir >= 0 && ia < h.nA && ia >= 0) atomicAdd(&h.evh[static_cast<size_t>(ir) * h.nA + ia], 1ull);
+    const double vxy2 = vx * vx + vy * vy;
+    const double cosang = vz / sqrt(vxy2 + vz * vz);
+    const int ic = hist_bin(cosang, h.c_first, h.c_step, h.inv_c);
+    if (ie < h.nEn && ie >= 0 && ic < h.nC && ic >= 0) {
+      if (ie < h.ea_rows) { const int k = ie * h.nC + ic; atomicAdd(&s_ea[k >> 1], 1u << ((k & 1) * 16)); }
+      else atomicAdd(&h.eah[static_cast<size_t>(ie) * h.nC + ic], 1ull);
+    }
+    const double vr = sqrt(vxy2);
+    const int ir = hist_bin(vr, 0.0, h.r_step, h.inv_r), ia = hist_bin(vz, h.a_first, h.a_step, h.inv_a);
+    if (ir < h.nR && ir >= 0 && ia < h.nA && ia >= 0) {
+      const int ja = ia - h.ev_a0;
+      if (ir < h.ev_rows && ja >= 0 && ja < h.ev_aw) { const int k = ir * h.ev_aw + ja; atomicAdd(&s_ev[k >> 1], 1u << ((k & 1) * 16)); }
+      else atomicAdd(&h.evh[static_cast<size_t>(ir) * h.nA + ia], 1ull);
+    }
   }
 }
 
-__device__ __forceinline__ void flush_energy_histogram(const HistGrid& h, const unsigned int* s_eeh) {
+__device__ __forceinline__ void clear_histogram_tiles(const HistGrid& h, unsigned int* s_eeh, unsigned int* s_ea) {
+  const int words = static_cast<int>(hist_tile_words(h));   // s_ev follows s_ea
+  for (int b = threadIdx.x; b < h.nEn; b += blockDim.x) s_eeh[b] = 0;
+  for (int b = threadIdx.x; b < words; b += blockDim.x) s_ea[b] = 0;
+}
+
+// CTA-private counts -> the global 64-bit accumulators (one atomic per non-empty bin and CTA)
+__device__ __forceinline__ void flush_histograms(const HistGrid& h, const unsigned int* s_eeh, const unsigned int* s_ea, const unsigned int* s_ev) {
   for (int b = threadIdx.x; b < h.nEn; b += blockDim.x) {
     const unsigned int c = s_eeh[b];
     if (c) {
       atomicAdd(&h.eeh[b], static_cast<unsigned long long>(c));
       if (h.eeh_phase) atomicAdd(&h.eeh_phase[b], static_cast<unsigned long long>(c));
     }
+  }
+  if (!h.cylindrical) return;
+  const int n_ea = h.ea_rows * h.nC, n_ev = h.ev_rows * h.ev_aw;
+  for (int w = threadIdx.x; 2 * w < n_ea; w += blockDim.x) {
+    const unsigned int c = s_ea[w];
+    if (c & 0xFFFFu) atomicAdd(&h.eah[2 * w], static_cast<unsigned long long>(c & 0xFFFFu));
+    if (c >> 16) atomicAdd(&h.eah[2 * w + 1], static_cast<unsigned long long>(c >> 16));
+  }
+  for (int w = threadIdx.x; 2 * w < n_ev; w += blockDim.x) {
+    const unsigned int c = s_ev[w];
+    const int k0 = 2 * w, k1 = 2 * w + 1;
+    if (c & 0xFFFFu) atomicAdd(&h.evh[static_cast<size_t>(k0 / h.ev_aw) * h.nA + h.ev_a0 + k0 % h.ev_aw], static_cast<unsigned long long>(c & 0xFFFFu));
+    if (c >> 16) atomicAdd(&h.evh[static_cast<size_t>(k1 / h.ev_aw) * h.nA + h.ev_a0 + k1 % h.ev_aw], static_cast<unsigned long long>(c >> 16));
   }
 }
 
@@ -170,12 +220,14 @@ __global__ void __launch_bounds__(ADV_THREADS, 2) k_advance(const Model m, const
   double* s_gain = reinterpret_cast<double*>(smem_raw);
   double* s_loss = s_gain + m.P;
   unsigned int* s_cnt = reinterpret_cast<unsigned int*>(s_loss + m.P);
-  unsigned int* s_eeh = s_cnt + m.P;
+  unsigned int* s_eeh = s_cnt + m.P;                                    // [nEn], then the two 2-D tiles
+  unsigned int* s_ea = s_eeh + h.nEn;
+  unsigned int* s_ev = s_ea + (static_cast<size_t>(h.ea_rows) * h.nC + 1) / 2;
   __shared__ double s_acc[ADV_WARPS][R_HEADER];
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int k = threadIdx.x; k < m.P; k += blockDim.x) { s_gain[k] = 0; s_loss[k] = 0; s_cnt[k] = 0; }
-  if (SAMPLE && h.enabled) for (int b = threadIdx.x; b < h.nEn; b += blockDim.x) s_eeh[b] = 0;
+  if (SAMPLE && h.enabled) clear_histogram_tiles(h, s_eeh, s_ea);
   for (int j = threadIdx.x; j < ADV_WARPS * R_HEADER; j += blockDim.x) (&s_acc[0][0])[j] = 0;
   __syncthreads();
 
@@ -275,7 +327,7 @@ __global__ void __launch_bounds__(ADV_THREADS, 2) k_advance(const Model m, const
     }
     if (SAMPLE) {
       sample_moments(alive, f.x, f.y, f.z, f.vx, f.vy, f.vz, f.eps, s_acc[warp], lane);
-      if (h.enabled && alive) sample_histograms(h, f.vx, f.vy, f.vz, f.eps, s_eeh);
+      if (h.enabled && alive) sample_histograms(h, f.vx, f.vy, f.vz, f.eps, s_eeh, s_ea, s_ev);
     }
   }
 
@@ -292,7 +344,7 @@ __global__ void __launch_bounds__(ADV_THREADS, 2) k_advance(const Model m, const
   }
   __syncthreads();
   write_partials(s_acc, s_cnt, s_gain, s_loss, m.P, partials);
-  if (SAMPLE && h.enabled) flush_energy_histogram(h, s_eeh);
+  if (SAMPLE && h.enabled) flush_histograms(h, s_eeh, s_ea, s_ev);
 }
 
 // FP64 roofline denominator: 16 independent DFMA chains per thread, nothing but the FP64 pipe (bench.py: roofline.fp64)
@@ -315,10 +367,12 @@ __global__ void __launch_bounds__(256) k_dfma_peak(double* out, int iters, doubl
 // ensemble sums + histograms as a separate pass (used when births/deaths can change the ensemble at t_sync)
 __global__ void __launch_bounds__(ADV_THREADS) k_sample(const State s, long long n, const HistGrid h, int P, double* __restrict__ partials) {
   extern __shared__ unsigned char smem_raw[];
-  unsigned int* s_eeh = reinterpret_cast<unsigned int*>(smem_raw);
+  unsigned int* s_eeh = reinterpret_cast<unsigned int*>(smem_raw);              // [nEn] EEDF row, then the tiles of the two 2-D grids
+  unsigned int* s_ea = s_eeh + h.nEn;
+  unsigned int* s_ev = s_ea + (static_cast<size_t>(h.ea_rows) * h.nC + 1) / 2;
   __shared__ double s_acc[ADV_WARPS][R_HEADER];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (h.enabled) for (int b = threadIdx.x; b < h.nEn; b += blockDim.x) s_eeh[b] = 0;
+  if (h.enabled) clear_histogram_tiles(h, s_eeh, s_ea);
   for (int j = threadIdx.x; j < ADV_WARPS * R_HEADER; j += blockDim.x) (&s_acc[0][0])[j] = 0;
   __syncthreads();
   double max_end = 0;
@@ -326,22 +380,23 @@ __global__ void __launch_bounds__(ADV_THREADS) k_sample(const State s, long long
 #pragma unroll
   for (int j = 0; j < N_SAMPLE_SUMS; ++j) val[j] = 0;
   // two electrons per iteration: twelve 8-byte streaming loads in flight per thread (six were not enough to cover HBM latency at 16 warps/SM:
-  // 4.5 TB/s in profiles/r1_v17_launches.csv)
+  // 4.5 TB/s in profiles/r1_v17_launches.csv).  The trip count is uniform over the CTA (the tiles are flushed at a barrier every HIST_PASS electrons).
   const long long stride = static_cast<long long>(gridDim.x) * ADV_THREADS;
-  for (long long i = blockIdx.x * static_cast<long long>(ADV_THREADS) + threadIdx.x; i < n; i += 2 * stride) {
-    const long long i2 = i + stride;
-    const bool two = i2 < n;
-    const long long j2 = two ? i2 : i;
+  int since_flush = 0;
+  for (long long base = blockIdx.x * static_cast<long long>(ADV_THREADS); base < n; base += 2 * stride) {
+    const long long i0 = base + threadIdx.x, i2 = i0 + stride;
+    const bool one = i0 < n, two = i2 < n;
+    const long long i = one ? i0 : 0, j2 = two ? i2 : i;
     const double x = __ldcs(&s.x[i]), y = __ldcs(&s.y[i]), z = __ldcs(&s.z[i]), vx = __ldcs(&s.vx[i]), vy = __ldcs(&s.vy[i]), vz = __ldcs(&s.vz[i]);
     const double xb = __ldcs(&s.x[j2]), yb = __ldcs(&s.y[j2]), zb = __ldcs(&s.z[j2]), vxb = __ldcs(&s.vx[j2]), vyb = __ldcs(&s.vy[j2]), vzb = __ldcs(&s.vz[j2]);
-    {
+    if (one) {
       const double eps = kinetic_eV(vx, vy, vz);
       max_end = fmax(max_end, eps);
       val[0] += eps; val[1] += x; val[2] += y; val[3] += z; val[4] += vx; val[5] += vy; val[6] += vz;
       val[7] += x * x; val[8] += x * y; val[9] += x * z; val[11] += y * y; val[12] += y * z; val[15] += z * z;
       val[16] += x * vx; val[17] += x * vy; val[18] += x * vz; val[19] += y * vx; val[20] += y * vy; val[21] += y * vz;
       val[22] += z * vx; val[23] += z * vy; val[24] += z * vz; val[25] += 1.0;
-      if (h.enabled) sample_histograms(h, vx, vy, vz, eps, s_eeh);
+      if (h.enabled) sample_histograms(h, vx, vy, vz, eps, s_eeh, s_ea, s_ev);
     }
     if (two) {
       const double eps = kinetic_eV(vxb, vyb, vzb);
@@ -350,7 +405,16 @@ __global__ void __launch_bounds__(ADV_THREADS) k_sample(const State s, long long
       val[7] += xb * xb; val[8] += xb * yb; val[9] += xb * zb; val[11] += yb * yb; val[12] += yb * zb; val[15] += zb * zb;
       val[16] += xb * vxb; val[17] += xb * vyb; val[18] += xb * vzb; val[19] += yb * vxb; val[20] += yb * vyb; val[21] += yb * vzb;
       val[22] += zb * vxb; val[23] += zb * vyb; val[24] += zb * vzb; val[25] += 1.0;
-      if (h.enabled) sample_histograms(h, vxb, vyb, vzb, eps, s_eeh);
+      if (h.enabled) sample_histograms(h, vxb, vyb, vzb, eps, s_eeh, s_ea, s_ev);
+    }
+    since_flush += 2 * ADV_THREADS;
+    if (h.enabled && since_flush + 2 * ADV_THREADS > HIST_PASS) {   // before a 16-bit counter can wrap
+      __syncthreads();
+      flush_histograms(h, s_eeh, s_ea, s_ev);
+      __syncthreads();
+      clear_histogram_tiles(h, s_eeh, s_ea);
+      __syncthreads();
+      since_flush = 0;
     }
   }
 #pragma unroll
@@ -363,7 +427,46 @@ __global__ void __launch_bounds__(ADV_THREADS) k_sample(const State s, long long
   if (lane == 0) s_acc[warp][R_MAX_EPS] = m0;
   __syncthreads();
   write_partials(s_acc, nullptr, nullptr, nullptr, P, partials);
-  if (h.enabled) flush_energy_histogram(h, s_eeh);
+  if (h.enabled) flush_histograms(h, s_eeh, s_ea, s_ev);
+}
+
+// getTimeDependDistributions' counting pass (BMC.C:1551-1571) on its own: only the three velocity columns are read (24 B per electron), there
+// are no running sums to keep in registers, so the kernel runs at full occupancy (the ensemble sums of the same sample come from k_sample
+// without a grid, inside the advance).
+constexpr int HIST_THREADS = 512;   // two CTAs per SM (their tiles take 79 KB each): 32 warps per SM
+__global__ void __launch_bounds__(HIST_THREADS, 2) k_histogram(const State s, long long n, const HistGrid h) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned int* s_eeh = reinterpret_cast<unsigned int*>(smem_raw);              // [nEn] EEDF row, then the tiles of the two 2-D grids
+  unsigned int* s_ea = s_eeh + h.nEn;
+  unsigned int* s_ev = s_ea + (static_cast<size_t>(h.ea_rows) * h.nC + 1) / 2;
+  clear_histogram_tiles(h, s_eeh, s_ea);
+  __syncthreads();
+  const long long stride = static_cast<long long>(gridDim.x) * HIST_THREADS;
+  int since_flush = 0;
+  for (long long base = blockIdx.x * static_cast<long long>(HIST_THREADS); base < n; base += 4 * stride) {   // uniform trip count over the CTA
+    double vx[4], vy[4], vz[4];
+    bool ok[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {   // twelve 8-byte streaming loads in flight per thread
+      const long long i = base + threadIdx.x + u * stride;
+      ok[u] = i < n;
+      const long long j = ok[u] ? i : 0;
+      vx[u] = __ldcs(&s.vx[j]); vy[u] = __ldcs(&s.vy[j]); vz[u] = __ldcs(&s.vz[j]);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) if (ok[u]) sample_histograms(h, vx[u], vy[u], vz[u], kinetic_eV(vx[u], vy[u], vz[u]), s_eeh, s_ea, s_ev);
+    since_flush += 4 * HIST_THREADS;
+    if (since_flush + 4 * HIST_THREADS > HIST_PASS) {   // before a 16-bit counter can wrap
+      __syncthreads();
+      flush_histograms(h, s_eeh, s_ea, s_ev);
+      __syncthreads();
+      clear_histogram_tiles(h, s_eeh, s_ea);
+      __syncthreads();
+      since_flush = 0;
+    }
+  }
+  __syncthreads();
+  flush_histograms(h, s_eeh, s_ea, s_ev);
 }
 
 // ------------------------------------------------------------------ K2: population control ------------------------------------------------------------------

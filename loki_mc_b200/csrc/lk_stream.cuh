@@ -29,7 +29,11 @@ constexpr int POOL = 1024;                       // electrons resident per CTA
 // Every per-slot array has PSTRIDE entries: slot POOL is a DUMMY that nobody ever writes after the kernel's prologue.  Lanes of the flight
 // phase that have no electron read it (their results are discarded), so no lane ever reads a slot that another warp may be writing:
 // compute-sanitizer racecheck is clean without predicated loads (tools/sanitize_stream.py).
+#ifdef LK_NO_DUMMY_SLOT
+constexpr int PSTRIDE = POOL;
+#else
 constexpr int PSTRIDE = POOL + 8;
+#endif
 constexpr int STREAM_THREADS = 256;
 constexpr int STREAM_WARPS = STREAM_THREADS / 32;
 static_assert(POOL == 4 * STREAM_THREADS, "the scan reads the 4 flags of a thread as one 32-bit word");
@@ -178,8 +182,10 @@ __global__ void __launch_bounds__(STREAM_THREADS, 2) k_advance_stream(const Mode
   if (tid < MC_COUNT) s_misc[tid] = 0;
   for (int j = tid; j < static_cast<int>(a.pad); j += STREAM_THREADS) reinterpret_cast<double*>(smem_raw + SM_NU)[j] = __ldg(&m.nu_tot[j]);
   reinterpret_cast<unsigned int*>(flag)[tid] = 0u;   // all slots FL_EMPTY
+#ifndef LK_NO_DUMMY_SLOT
   if (tid < SC_COLS) col[tid * PSTRIDE + POOL] = 0.0;   // the dummy slot (never written again)
   if (tid == 0) { s_used[POOL] = 0u; flag[POOL] = FL_EMPTY; }
+#endif
 
   // the CTA's range [lo, lo + len) of the ensemble; cursors are CTA-uniform offsets into it.  Column c of the state is sid.s.x + lo + c * a.n.
   if (tid == 0) {
@@ -379,7 +385,11 @@ __global__ void __launch_bounds__(STREAM_THREADS, 2) k_advance_stream(const Mode
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
           Flyer& f = e[j];
+#ifdef LK_NO_DUMMY_SLOT
+          int sl = 0; bool act = false;
+#else
           int sl = POOL; bool act = false;   // no electron: the dummy slot
+#endif
           const int item = 2 * it + j;
           if (item < nK) { const int k = 32 * (warp + 8 * item) + lane; if (k < nB) { sl = listR[k]; act = true; } }
           else if (item < nA) { const int k = 32 * (wrot + 8 * (item - nK)) + lane; if (k < nFlr) { sl = listF[k]; act = true; } }

@@ -163,7 +163,7 @@ double lin_interp(const double* x, const double* y, int64_t n, double xv) {
 }
 
 size_t adv_smem_bytes(const lokib200_engine* h, bool sample) {
-  return static_cast<size_t>(h->P) * (8 + 8 + 4) + ((sample && h->hist.enabled) ? static_cast<size_t>(h->hist.nEn) * 4 : 0) + 16;
+  return static_cast<size_t>(h->P) * (8 + 8 + 4) + ((sample && h->hist.enabled) ? (static_cast<size_t>(h->hist.nEn) + hist_tile_words(h->hist)) * 4 : 0) + 16;
 }
 
 template <int F, int G, bool S>
@@ -876,6 +876,7 @@ int lokib200_regrid_energy_histograms(lokib200_engine* h, double new_max) {
   HistGrid& g = h->hist;
   h->hist_reduced = false;
   g.e_step = (0.0 + 1 * (new_max - 0.0) / static_cast<double>(g.nEn)) - 0.0;   // BMC.C:1507-1508
+  g.inv_e = 1.0 / g.e_step;
   h->max_eedf_energy = new_max;
   const size_t ne = g.nEn;
   CK(cudaMemsetAsync(h->d_eeh, 0, ne * 8, h->stream)); CK(cudaMemsetAsync(h->d_eah, 0, ne * g.nC * 8, h->stream));
@@ -900,6 +901,12 @@ int lokib200_set_histogram_grid(lokib200_engine* h, double max_eedf_energy) {
   g.r_step = (0.0 + 1 * (max_speed - 0.0) / static_cast<double>(g.nR)) - 0.0;
   g.a_first = -max_speed; g.a_step = (-max_speed + 1 * (max_speed - (-max_speed)) / static_cast<double>(g.nA)) - g.a_first;
   h->max_eedf_energy = max_eedf_energy;
+  // shared-memory tiles of the 2-D grids: the lowest 256 energy rows, and the 96 innermost radial rows x the 128 central axial cells (75 KB)
+  g.ea_rows = c.is_cylindrically_symmetric ? std::min(g.nEn, 256) : 0;
+  g.ev_rows = c.is_cylindrically_symmetric ? std::min(g.nR, 96) : 0;
+  g.ev_aw = c.is_cylindrically_symmetric ? std::min(g.nA, 128) : 0;
+  g.ev_a0 = (g.nA - g.ev_aw) / 2;
+  g.inv_e = 1.0 / g.e_step; g.inv_c = 1.0 / g.c_step; g.inv_r = 1.0 / g.r_step; g.inv_a = 1.0 / g.a_step;
   const size_t ne = g.nEn, nea = ne * g.nC, nev = static_cast<size_t>(g.nR) * g.nA, nep = ne * c.n_phases;
   if (!h->d_eeh) {
     CK(cudaMalloc(&h->d_eeh, ne * 8)); CK(cudaMalloc(&h->d_eah, nea * 8)); CK(cudaMalloc(&h->d_evh, nev * 8)); CK(cudaMalloc(&h->d_eeh_per, nep * 8));
@@ -919,7 +926,12 @@ int lokib200_sample_histograms(lokib200_engine* h, int32_t phase_index) {
   HistGrid g = h->hist;
   h->hist_reduced = false;
   g.eeh_phase = (phase_index >= 0) ? h->d_eeh_per + static_cast<size_t>(phase_index) * g.nEn : nullptr;
-  k_sample<<<h->smp_blocks, ADV_THREADS, static_cast<size_t>(g.nEn) * 4 + 16, h->stream>>>(h->st, h->cfg.n_electrons, g, h->P, h->d_smp_part);
+  const size_t hsmem = (static_cast<size_t>(g.nEn) + hist_tile_words(g)) * 4 + 16;
+  static bool attr_set[64] = {};
+  if (!attr_set[h->cfg.device & 63]) { CK(cudaFuncSetAttribute(k_histogram, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); attr_set[h->cfg.device & 63] = true; }
+  if (hsmem > 100 * 1024) return fail(h, LOKIB200_ERR_INVALID, "histogram grids too fine for the shared-memory tiles");
+  const int hblocks = static_cast<int>(std::min<int64_t>((h->cfg.n_electrons + HIST_THREADS - 1) / HIST_THREADS, static_cast<int64_t>(h->sm_count) * 2));
+  k_histogram<<<hblocks, HIST_THREADS, hsmem, h->stream>>>(h->st, h->cfg.n_electrons, g);
   ++h->launches;
   CK(cudaGetLastError());
   return 0;

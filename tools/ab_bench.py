@@ -10,7 +10,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 libs = sys.argv[1:] or sorted(glob.glob(os.path.join(ROOT, "build", "variants", "lib_*.so")))
 for lib in libs:
     env = dict(os.environ, LOKIB200_LIB=lib)
-    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--no-cpu-baseline", "--steps", "30", "--relax", "30"], env=env,
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--no-cpu-baseline", "--no-extras", "--steps", "30", "--relax", "30"], env=env,
                        stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     try:
         d = json.loads(r.stdout.strip().split("\n")[-1])
