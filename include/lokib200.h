@@ -226,6 +226,11 @@ int lokib200_check_nu_trial(lokib200_engine* h, double max_energy, double horizo
 /* which form of the advance kernel this engine launches: 0 = one electron per thread (k_advance, small ensembles), 1 = streaming pool in
  * shared memory (k_advance_stream, large ensembles); the choice is made in lokib200_set_processes from n_electrons and the SM count */
 int32_t lokib200_kernel_form(const lokib200_engine* h);
+/* Fast mode (not a reference feature; off by default = the reference's single trial collision frequency, BMC.C:716-763).  When on, every free
+ * time is drawn against the trial frequency of the electron's energy band (half octaves; the maximum of nu_tot over all energies reachable within
+ * a look-ahead time, from the same tables and the same acceleration bound) and a flight that outlasts the look-ahead time is cut and redrawn.
+ * Same physics, far fewer null collisions; the event counters then count fewer (null) events per unit of physical time. */
+int lokib200_set_fast_mode(lokib200_engine* h, int32_t on);
 /* nominal HBM bandwidth of the engine's device [GB/s] from its memory clock and bus width (status display: fraction of the roofline) */
 double lokib200_device_hbm_gbs(const lokib200_engine* h);
 /* number of kernels launched by this engine so far (bench.py's gpu_launches) */

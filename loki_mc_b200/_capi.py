@@ -149,7 +149,7 @@ SYMBOLS = ["lokib200_abi_version", "lokib200_device_count", "lokib200_create", "
            "lokib200_job_process_outputs", "lokib200_job_time_series", "lokib200_job_histograms", "lokib200_job_periodic",
            "lokib200_job_periodic_diffusion", "lokib200_job_conditions", "lokib200_job_evdf_max_speed", "lokib200_job_last_error", "lokib200_job_destroy",
            "lokib200_sample_moments_device", "lokib200_comm_unique_id", "lokib200_comm_init_rank", "lokib200_comm_init_all", "lokib200_comm_destroy",
-           "lokib200_comm_size", "lokib200_comm_allreduce_results", "lokib200_comm_allreduce_histograms", "lokib200_kernel_form", "lokib200_device_hbm_gbs"]
+           "lokib200_comm_size", "lokib200_comm_allreduce_results", "lokib200_comm_allreduce_histograms", "lokib200_kernel_form", "lokib200_device_hbm_gbs", "lokib200_set_fast_mode"]
 # every symbol include/lokib200_host.h declares
 HOST_SYMBOLS = ["lokib200_setup_load", "lokib200_setup_destroy", "lokib200_setup_last_error", "lokib200_setup_job_count", "lokib200_setup_job_value",
                 "lokib200_setup_variable_condition", "lokib200_setup_processes", "lokib200_setup_config", "lokib200_setup_controls",
@@ -195,6 +195,7 @@ def lib():
     L.lokib200_launch_count.argtypes = [vp]; L.lokib200_launch_count.restype = C.c_int64
     L.lokib200_kernel_form.argtypes = [vp]; L.lokib200_kernel_form.restype = C.c_int32
     L.lokib200_device_hbm_gbs.argtypes = [vp]; L.lokib200_device_hbm_gbs.restype = C.c_double
+    L.lokib200_set_fast_mode.argtypes = [vp, C.c_int32]
     L.lokib200_kernel_time_ms.argtypes = [vp, c_dp, c_lp]
     L.lokib200_measure_fp64_peak.argtypes = [vp, c_dp]
     L.lokib200_sample_moments.argtypes = [vp, c_dp]
@@ -439,6 +440,10 @@ class Engine:
         self._check(self.L.lokib200_check_nu_trial(self.h, float(max_energy), float(horizon), self.energy_max_elastic, C.byref(nu)))
         return nu.value
 
+    def set_fast_mode(self, on=True):
+        """per-energy-band trial collision frequencies (not a reference feature; see include/lokib200.h)"""
+        self._check(self.L.lokib200_set_fast_mode(self.h, int(bool(on))))
+
     def launch_count(self):
         return int(self.L.lokib200_launch_count(self.h))
 
@@ -496,6 +501,9 @@ class Job:
         c.initial_temp_ratio = float(initial_temp_ratio); c.energy_max_elastic = float(self.engines[0].energy_max_elastic)
         c.max_intervals = int(max_intervals)
         c.status_display = int(kw.get("status_display", 0)); c.fast_mode = int(kw.get("fast_mode", 0))
+        for k in ("min_collisions_before_ss", "max_collisions_before_ss", "max_collisions_after_ss"):
+            if k in kw:
+                setattr(c, k, float(kw[k]))
         for k in ("rel_err_mean_energy", "rel_err_flux_drift", "rel_err_flux_diff", "rel_err_bulk_drift", "rel_err_bulk_diff", "rel_err_power_balance"):
             if k in kw:
                 setattr(c, k, float(kw[k])); c.errors_to_be_checked = 1
@@ -528,6 +536,13 @@ class Job:
         t = np.zeros(n); me = np.zeros(n); mp = np.zeros((n, 3)); mv = np.zeros((n, 3)); pc = np.zeros((n, 9))
         self.L.lokib200_job_time_series(self.h, _dp(t), _dp(me), _dp(mp), _dp(mv), _dp(pc))
         return dict(times=t, mean_energy=me, mean_position=mp, mean_velocity=mv, position_covariance=pc)
+
+    def periodic(self):
+        """phase-resolved averages of an AC job (lokib200_job_periodic)"""
+        nph = self.engines[0].cfg.n_phases
+        pts = np.zeros(nph); me = np.zeros(nph); fv = np.zeros((nph, 3)); bv = np.zeros((nph, 3))
+        self.L.lokib200_job_periodic(self.h, _dp(pts), _dp(me), _dp(fv), _dp(bv))
+        return dict(points_per_phase=pts, mean_energy=me, flux_velocity=fv, bulk_velocity=bv)
 
     def histograms(self):
         c = self.engines[0].cfg

@@ -145,10 +145,10 @@ struct Flyer {   // one electron in the flight phase (two per lane)
   unsigned int used;
   int sl;
   unsigned char outcome;
-  bool active, need, clamped, exceeded;
+  bool active, need, clamped, exceeded, virt;
 };
 
-enum : int { MC_BORN = 0, MC_ATT, MC_CLAMP, MC_NUEX, MC_COUNT };   // rare events: counted with shared atomics, not in registers
+enum : int { MC_BORN = 0, MC_ATT, MC_CLAMP, MC_NUEX, MC_VIRT, MC_COUNT };   // rare events: counted with shared atomics, not in registers
 // CTA-uniform state of a round lives in shared memory and is re-read where it is used: with 128 registers per thread every value that stays
 // live across the inlined collision code is a spill candidate, and local-memory spills miss the small L1 (profiles/r1_v10_*)
 enum : int { RS_IN = 0, RS_OUT, RS_LEN, RS_NFL, RS_NBC, RS_NBT, RS_NRET, RS_NREFILL, RS_COUNT };   // (the 64-bit ones, range start and flight count, sit in s_scan[8], s_scan[9])
@@ -417,8 +417,14 @@ __global__ void __launch_bounds__(STREAM_THREADS, 2) k_advance_stream(const Mode
         if (any_draw) {
 #pragma unroll
           for (int j = 0; j < 2; ++j) {
-            const double drawn = div_by(-log_normal(u0[j]), a.nu_trial, rnu);   // -log(u) / nu_trial, BMC.C:650-655
-            if (e[j].need) { e[j].p.tcf = drawn; e[j].p.nue = a.nu_trial; ++e[j].used; }
+            double nu = a.nu_trial, r = rnu, tau = 0;
+            if (m.banded) {   // fast mode (CTA-uniform branch): trial frequency and look-ahead time of the electron's energy band, see draw_free_time
+              const int b = energy_band(kinetic_eV(e[j].p.vx, e[j].p.vy, e[j].p.vz));
+              nu = m.band_nu[b]; tau = m.band_tau[b]; r = recip_for_div(nu);
+            }
+            const double drawn = div_by(-log_normal(u0[j]), nu, r);   // -log(u) / nu_trial, BMC.C:650-655
+            const bool cut = m.banded && drawn > tau;
+            if (e[j].need) { e[j].p.tcf = cut ? tau : drawn; e[j].p.nue = cut ? -nu : nu; ++e[j].used; }
           }
         }
         double seen = 0;
@@ -435,14 +441,16 @@ __global__ void __launch_bounds__(STREAM_THREADS, 2) k_advance_stream(const Mode
           const bool thermal = thermal_branch<GT>(m, p.eps);
           double Rnu; bool clamped, exceeded;
           const bool real = stream_null_test(m, s_nu, staged_rows, p.eps, p.nue, u_null, Rnu, clamped, exceeded);
-          const bool tested = !partial && !thermal;                  // the thermal-target branch draws its own numbers in (3)
-          f.outcome = partial ? FL_DONE : thermal ? FL_REALT : real ? FL_REAL : FL_FLIGHT;
+          const bool virt = p.nue < 0;                               // fast mode: the flight was cut at the band's look-ahead time, nothing is tested
+          const bool tested = !partial && !thermal && !virt;         // the thermal-target branch draws its own numbers in (3)
+          f.outcome = partial ? FL_DONE : virt ? FL_FLIGHT : thermal ? FL_REALT : real ? FL_REAL : FL_FLIGHT;
           const double t_event = p.t + p.tcf;
           p.tcf = partial ? (p.tcf - dt) : (tested && real) ? Rnu : NON_DEF;
           p.t = partial ? a.t_sync : t_event;
           f.used += tested ? 1u : 0u;
           f.clamped = f.active && tested && clamped; f.exceeded = f.active && tested && exceeded;
-          rare = rare || f.clamped || f.exceeded;
+          f.virt = f.active && virt && !partial;
+          rare = rare || f.clamped || f.exceeded || f.virt;
           if (f.active) seen = fmax(seen, p.eps);
         }
 #pragma unroll
@@ -460,7 +468,7 @@ __global__ void __launch_bounds__(STREAM_THREADS, 2) k_advance_stream(const Mode
         }
         if (rare) {
 #pragma unroll
-          for (int j = 0; j < 2; ++j) { if (e[j].clamped) atomicAdd(&s_misc[MC_CLAMP], 1u); if (e[j].exceeded) atomicAdd(&s_misc[MC_NUEX], 1u); }
+          for (int j = 0; j < 2; ++j) { if (e[j].clamped) atomicAdd(&s_misc[MC_CLAMP], 1u); if (e[j].exceeded) atomicAdd(&s_misc[MC_NUEX], 1u); if (e[j].virt) atomicAdd(&s_misc[MC_VIRT], 1u); }
         }
         seen_round = fmax(seen_round, seen);
       }
@@ -479,7 +487,7 @@ __global__ void __launch_bounds__(STREAM_THREADS, 2) k_advance_stream(const Mode
     // events = non-partial flights = (flights flown) - (electrons of the range); null = events - real  (BMC.C:1308-1320)
     const unsigned long long flights = *reinterpret_cast<volatile unsigned long long*>(&s_scan[9]) - s_misc[MC_ATT];
     const unsigned long long partials_n = static_cast<unsigned long long>(s_rs[RS_LEN]) - s_misc[MC_ATT];
-    s_hdr[R_N_NULL] = static_cast<double>(flights - partials_n) - nr;
+    s_hdr[R_N_NULL] = static_cast<double>(flights - partials_n) - nr - static_cast<double>(s_misc[MC_VIRT]);   // (cut flights of the fast mode are not trial events)
     s_hdr[R_N_BORN] = static_cast<double>(s_misc[MC_BORN]); s_hdr[R_N_ATTACHED] = static_cast<double>(s_misc[MC_ATT]);
     s_hdr[R_N_TABLE_CLAMPED] = static_cast<double>(s_misc[MC_CLAMP]); s_hdr[R_N_NU_EXCEEDED] = static_cast<double>(s_misc[MC_NUEX]);
     double gf = 0, m0 = 0, m1 = 0;

@@ -74,6 +74,11 @@ struct lokib200_engine {
   bool use_tile = false;   // a shared-memory kernel (stream or lane) instead of one electron per thread
   int last_adv_blocks = 0;
 
+  // fast mode: trial frequency per energy band (lk_physics.cuh draw_free_time); the tables are rebuilt when the trial frequency or the cross-section tables change
+  bool fast_mode = false;
+  double band_nu[N_BANDS] = {}, band_tau[N_BANDS] = {}, band_for_nu = 0;
+  uint64_t table_version = 0, band_for_version = ~0ull;
+
   // multi-GPU: communicator over the shards of one job (null = none)
   ncclComm_t comm = nullptr;
   int comm_size = 1, comm_rank = 0;
@@ -148,6 +153,8 @@ Model make_model(const lokib200_engine* h) {
   }
   m.cum = h->d_cum; m.nu_tot = h->d_nu_tot;
   m.pair = h->d_pair;
+  m.banded = h->fast_mode ? 1 : 0;
+  if (h->fast_mode) { std::memcpy(m.band_nu, h->band_nu, sizeof(m.band_nu)); std::memcpy(m.band_tau, h->band_tau, sizeof(m.band_tau)); }
   m.type = h->d_type; m.angular = h->d_angular; m.ap0 = h->d_ap0; m.ap1 = h->d_ap1; m.mass = h->d_mass; m.redmass = h->d_redmass;
   m.eloss = h->d_eloss; m.thstd = h->d_thstd; m.wpar = h->d_wpar; m.gas_first = h->d_gas_first; m.gas_last = h->d_gas_last;
   m.gas_fraction = h->d_gas_fraction;
@@ -357,12 +364,15 @@ int push_tables(lokib200_engine* h) {   // h_cum (padded) / h_nu_tot -> device
   CK(cudaMemcpyAsync(h->d_nu_tot, h->h_nu_tot.data(), need_nu * sizeof(double), cudaMemcpyHostToDevice, h->stream));
   CK(cudaStreamSynchronize(h->stream));
   h->have_tables = true;
+  ++h->table_version;
   return 0;
 }
 
 }  // namespace
 
 extern "C" {
+
+static void build_bands(lokib200_engine* h, double nu_trial);
 
 int lokib200_abi_version(void) { return LOKIB200_ABI_VERSION; }
 
@@ -671,6 +681,7 @@ int lokib200_advance_to_sync_device(lokib200_engine* h, double nu_trial, double 
   if (rc) return rc;
   if (!(nu_trial > 0) || !(t_sync > h->time)) return fail(h, LOKIB200_ERR_INVALID, "need nu_trial > 0 and t_sync > current time");
   CK(cudaSetDevice(h->cfg.device));
+  if (h->fast_mode && (h->band_for_nu != nu_trial || h->band_for_version != h->table_version)) build_bands(h, nu_trial);
   const Model m = make_model(h);
   ++h->interval;
   AdvArgs a{};
@@ -1037,6 +1048,39 @@ int lokib200_check_nu_trial(lokib200_engine* h, double max_energy_now, double ho
     const int idx = static_cast<int>(std::fmin(std::ceil(maxE / h->dE), static_cast<double>(h->nE - 1)));   // BMC.C:754
     if (*nu_trial < h->h_nu_max[idx]) { updated = true; *nu_trial *= 1.1; }   // BMC.C:758-761
   }
+  return 0;
+}
+
+// Fast mode: per half-octave band [.., Eu) the smallest trial frequency that bounds nu_tot over every energy an electron starting below Eu
+// can reach within the look-ahead time tau = 3 / nu (fixed point of nu = max nu_tot up to maximizationAccelerationEnergy(Eu, 3 / nu) + the
+// thermal margin of checkMaxCollisionFrequency, BMC.C:724-737), never above the global trial frequency, which needs no look-ahead limit.
+static void build_bands(lokib200_engine* h, double nu_trial) {
+  const int gt = h->cfg.gas_temperature_effect;
+  const double thermal = (gt == GT_TRUE || gt == GT_SMART) ? 10.0 * (1.5 * KB * h->cfg.gas_temperature / QE) : 0.0;
+  auto maxnu = [&](double E) { return h->h_nu_max[static_cast<int>(std::fmin(std::ceil(E / h->dE), static_cast<double>(h->nE - 1)))]; };
+  for (int b = 0; b < N_BANDS; ++b) {
+    const double Eu = std::ldexp(1.0, -12) * std::pow(2.0, 0.5 * (b + 1));
+    double nu = nu_trial, tau = 1e300;
+    if (Eu + thermal < h->maxE) {
+      double cand = maxnu(Eu + thermal);
+      for (int it = 0; it < 64 && cand < nu_trial; ++it) {
+        const double reach = lokib200_max_accel_energy(h, Eu, 3.0 / cand) + thermal;
+        if (reach >= h->maxE) { cand = nu_trial; break; }
+        const double next = maxnu(reach);
+        if (next <= cand) break;
+        cand = next;
+      }
+      if (cand < nu_trial) { nu = cand; tau = 3.0 / cand; }
+    }
+    h->band_nu[b] = nu; h->band_tau[b] = tau;
+  }
+  h->band_for_nu = nu_trial; h->band_for_version = h->table_version;
+}
+
+int lokib200_set_fast_mode(lokib200_engine* h, int32_t on) {
+  if (!h) return LOKIB200_ERR_INVALID;
+  h->fast_mode = on != 0;
+  h->band_for_version = ~0ull;
   return 0;
 }
 

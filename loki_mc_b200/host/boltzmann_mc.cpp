@@ -377,6 +377,7 @@ struct lokib200_job {
     solveStart = start;
     // ---- evaluateNonConstantVariables (BMC.C:428-559) ----
     time = 0; steadyStateTime = NON_DEF;
+    for (auto* e : engines) lokib200_set_fast_mode(e, ctl.fast_mode);
     double maxInit = 0;
     for (auto* e : engines) {
       double mx = 0;

@@ -28,8 +28,14 @@ def _ref(name):
 STREAM_CASES = ["reid_acb", "n2_aniso", "o2_sdcs", "arhe", "ls_att_aniso"]
 
 
-@pytest.mark.parametrize("name,kernel", [(c, "auto") for c in CASES] + [(c, "stream") for c in STREAM_CASES])
-def test_swarm_parameters_within_3_sigma(name, kernel, monkeypatch):
+# ... and with per-energy-band trial frequencies (fast mode, not a reference feature): the same physics with far fewer null collisions, so the
+# swarm parameters must still agree with the reference within 3 sigma while the real-collision fraction goes up
+FAST_CASES = [("reid_dc", "auto"), ("n2_aniso", "auto"), ("n2_aniso", "stream"), ("o2_sdcs", "auto"), ("air", "stream"), ("ls_f05", "auto"), ("reid_acb", "stream"),
+              ("reid_true_aniso", "auto")]
+
+
+@pytest.mark.parametrize("name,kernel,fast", [(c, "auto", 0) for c in CASES] + [(c, "stream", 0) for c in STREAM_CASES] + [(c, k, 1) for c, k in FAST_CASES])
+def test_swarm_parameters_within_3_sigma(name, kernel, fast, monkeypatch):
     import loki_mc_b200 as lk
     if kernel != "auto":
         monkeypatch.setenv("LOKIB200_KERNEL", kernel)
@@ -37,8 +43,9 @@ def test_swarm_parameters_within_3_sigma(name, kernel, monkeypatch):
     ref = _ref(name)
     n = 10 * ref["n_electrons"]
     eng = lk.Engine(g, n, seed=20240 + len(name))
-    job = lk.Job([eng], n_integration_points=ref["n_integration_points"], n_integrated_ss_times=ref["n_integrated_ss_times"])
+    job = lk.Job([eng], n_integration_points=ref["n_integration_points"], n_integrated_ss_times=ref["n_integrated_ss_times"], fast_mode=fast)
     r = job.solve()
+    assert r["n_nu_exceeded"] <= 1e-4 * (r["total_collisions"] + r["null_collisions"])   # the trial frequencies (global or per band) bound nu_tot
     Ngas = g["cond"]["gas_density"]
     assert r["steady_state_time"] > 0 and r["n_integration_points"] >= ref["n_integration_points"]
 
@@ -65,6 +72,47 @@ def test_swarm_parameters_within_3_sigma(name, kernel, monkeypatch):
     ref_frac = np.mean([x["real"] / (x["real"] + x["null"]) for x in ref["replicas"]])
     ours_frac = r["total_collisions"] / (r["total_collisions"] + r["null_collisions"])
     # (depends on the value nu_trial settles at, which differs slightly: our energy bound looks one interval further ahead)
-    assert abs(ours_frac - ref_frac) < 0.25 * ref_frac, (ours_frac, ref_frac)
+    if fast:
+        assert ours_frac > ref_frac, (ours_frac, ref_frac)     # fewer null collisions for the same real ones
+        print("fast mode %s: real-collision fraction %.3f (reference %.3f), %.3g events" % (name, ours_frac, ref_frac, r["total_collisions"] + r["null_collisions"]))
+    else:
+        assert abs(ours_frac - ref_frac) < 0.25 * ref_frac, (ours_frac, ref_frac)
     assert r["power_balance_rel_error"] < 5e-3
+    job.close(); eng.close()
+
+
+def test_phase_resolved_parameters_ac_field_with_magnetic_field():
+    """BASELINE.json configs[3]: N2 in an AC electric field crossed with a DC magnetic field, gasTemperatureEffect true.  Whole job against the
+    reference's replicas: time averages within 3 sigma, and the mean energy and flux velocity PER PHASE of the field (MCTemporalInfo_periodic,
+    Output.h:756-782; BoltzmannMC.C:1468-1481) within 4 sigma of the replicas' scatter in every one of the 100 phase bins."""
+    import loki_mc_b200 as lk
+    g = gio.load("n2_true_acb")
+    ref = _ref("n2_true_acb")
+    n = 10 * ref["n_electrons"]
+    eng = lk.Engine(g, n, seed=777)
+    # (the reference's steady-state criterion can take arbitrarily long for AC fields at low noise: both sides cap it, DESIGN.md section 9)
+    job = lk.Job([eng], n_integration_points=ref["n_integration_points"], n_integrated_ss_times=0.0, max_collisions_before_ss=2e3 * n)
+    r = job.solve()
+    mean, std = ref["mean"]["Energy parameters/Mean energy"], ref["std"]["Energy parameters/Mean energy"]
+    sig = np.sqrt(max(std, 2e-3 * mean) ** 2 + r["averaged_mean_energy_error"] ** 2)
+    assert abs(r["averaged_mean_energy"] - mean) <= 3 * sig, (r["averaged_mean_energy"], mean, sig)
+    per = job.periodic()
+    pm, ps = np.array(ref["periodic"]["mean"]), np.array(ref["periodic"]["std"])
+    # (the sample at which the steady state is detected opens the integration but is not phase-binned: BoltzmannMC.C:1468 tests steadyStateTime first)
+    assert r["n_integration_points"] - 1 <= per["points_per_phase"].sum() <= r["n_integration_points"] and per["points_per_phase"].min() > 0
+    # three replicas give a noisy scatter estimate: floor it with the typical scatter over all phases
+    e_sig = np.maximum(ps[:, 3], np.median(ps[:, 3])) * np.sqrt(1 + 0.1)
+    assert np.all(np.abs(per["mean_energy"] - pm[:, 3]) <= 4 * e_sig + 2e-3 * pm[:, 3]), np.abs(per["mean_energy"] - pm[:, 3]).max()
+    for c, a in ((4, 0), (5, 1)):      # v_x, v_y follow the rotating E x B drift; v_z is zero within noise (E is along x)
+        v_sig = np.maximum(ps[:, c], np.median(ps[:, c])) * np.sqrt(1 + 0.1)
+        amp = np.abs(pm[:, c]).max()
+        assert np.all(np.abs(per["flux_velocity"][:, a] - pm[:, c]) <= 4 * v_sig + 5e-3 * amp), (c, np.abs(per["flux_velocity"][:, a] - pm[:, c]).max(), amp)
+    # the phase-resolved EEDF rows hold exactly one count per electron and sample of that phase, and their mean energy is the phase's mean energy
+    h = job.histograms()
+    rows = h["eeh_periodic"].sum(axis=1)
+    # (every sample is counted, including the one that opened the integration: one phase row holds one sample more than points_per_phase)
+    assert np.all(rows >= per["points_per_phase"] * n) and np.all(rows <= (per["points_per_phase"] + 1) * n) and rows.sum() == r["n_integration_points"] * n
+    centres = (np.arange(h["eeh_periodic"].shape[1]) + 0.5) * r["max_eedf_energy"] / h["eeh_periodic"].shape[1]
+    e_from_hist = (h["eeh_periodic"] * centres).sum(axis=1) / rows
+    assert np.all(np.abs(e_from_hist - per["mean_energy"]) <= 2e-2 * per["mean_energy"])
     job.close(); eng.close()

@@ -276,6 +276,17 @@ def test_full_size_energy_balance(name, n):
                                              ("arhe_true", 60.0, 150.0), ("air", 40.0, 100.0), ("ls_att_aniso", 40.0, 100.0),
                                              ("n2_true_acb", 30.0, 60.0)] + [(nm, 5.0, 12.0) for nm in gio.FIELD_GT_MODELS])
 def test_tile_kernel_equals_thread_kernel(name, e_hi, maxE, monkeypatch):
+    _tile_equals_thread(name, e_hi, maxE, monkeypatch, fast=False)
+
+
+@pytest.mark.parametrize("name,e_hi,maxE", [("n2_aniso", 60.0, 150.0), ("reid_acb_smart", 5.0, 12.0), ("reid_ecr_true", 5.0, 12.0), ("air", 40.0, 100.0)])
+def test_tile_kernel_equals_thread_kernel_fast_mode(name, e_hi, maxE, monkeypatch):
+    """per-energy-band trial frequencies (fast mode): both kernel forms must implement the same band lookup, the same cut of a flight at the
+    band's look-ahead time and the same draw positions, i.e. agree bit for bit again"""
+    _tile_equals_thread(name, e_hi, maxE, monkeypatch, fast=True)
+
+
+def _tile_equals_thread(name, e_hi, maxE, monkeypatch, fast):
     """the shared-memory kernel (streaming pool, production for large ensembles) and the one-thread-per-electron kernel consume the same per-electron
     draw streams, so they must produce the same ensemble bit for bit and the same event counters -- also when electrons are
     born (ionization) or lost (attachment): only the slots touched by the population control at t_sync may differ."""
@@ -290,6 +301,7 @@ def test_tile_kernel_equals_thread_kernel(name, e_hi, maxE, monkeypatch):
         monkeypatch.setenv("LOKIB200_KERNEL", kern)
         eng = _engine(g, n, seed=4242, first_electron_id=10)
         eng.build_tables(maxE)
+        eng.set_fast_mode(fast)
         nu = eng.table_info()["nu_max_last"]
         eng.set_ensemble(s0, 0.0)
         res = [eng.advance(nu, 1 / nu, sample=True)]
