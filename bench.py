@@ -274,12 +274,13 @@ class Arm:
     """One engine per rank on one explicit torch stream; for world > 1 the shards of the job share a communicator INSIDE the engine
     (lokib200_comm_init_rank): torch.distributed only carries the 128-byte NCCL id, the barrier and the max-over-ranks of the timings."""
 
-    def __init__(self, torch, dist, lk, model, n, rank, world, local, stream):
+    def __init__(self, torch, dist, lk, model, n, rank, world, local, stream, fast=False):
         self.torch, self.dist, self.lk, self.rank, self.world = torch, dist, lk, rank, world
         self.g = load_model(model)
         self.model, self.n = model, n
         self.eng = lk.Engine(self.g, n, seed=0x4C6F4B49, device=local, first_electron_id=rank * n)
         self.eng.set_stream(stream.cuda_stream)
+        self.eng.set_fast_mode(fast)
         if world > 1:
             idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
             if rank == 0:
@@ -441,11 +442,13 @@ def main():
         # more of what BASELINE.json names, each a short leg of the same measurement (same rules: warm-up >= 3, inputs >> L2, CUDA events)
         extra = [dict(tag="configs[1] with histograms every sample (post-steady-state cadence, BoltzmannMC.C:1551-1571)", model=args.model, n=n, S=1.0, hist=True, steps=20),
                  dict(tag="configs[1] at synchronizationTimeXMaxCollisionFrequency = 10 (Headers/BoltzmannMC.h:72)", model=args.model, n=n, S=10.0, hist=False, steps=10),
+                 dict(tag="configs[1] in fast mode (per-energy-band trial frequencies, not a reference feature): fewer null events for the same physics", model=args.model, n=n,
+                      S=1.0, hist=False, steps=20, fast=True),
                  dict(tag="configs[4] air, 1e9 electrons over 8 GPUs = 1.25e8 per GPU", model="air", n=125_000_000, S=1.0, hist=False, steps=10),
                  dict(tag="configs[2] Ar/He ionization growth, 1e8 electrons over 8 GPUs = 1.25e7 per GPU", model="arhe", n=12_500_000, S=1.0, hist=False, steps=20),
                  dict(tag="reference-size ensemble (1e5 electrons, configs[0] process set)", model="o2_sdcs", n=100_000, S=1.0, hist=False, steps=100)]
         for x in extra:
-            a2 = Arm(torch, dist, lk, x["model"], x["n"], rank, world, local, stream)
+            a2 = Arm(torch, dist, lk, x["model"], x["n"], rank, world, local, stream, fast=x.get("fast", False))
             mm = a2.measure(x["steps"], 3, 40 if x["n"] <= 12_500_000 else 25, S=x["S"], hist=x["hist"])
             a2.close()
             if rank == 0:
@@ -453,7 +456,7 @@ def main():
                 also.append(dict(workload=x["tag"], process_set=x["model"], electrons_per_gpu=x["n"], sync_factor=x["S"], histograms=x["hist"], steps=x["steps"],
                                  value=mm["ev_dev"] / (mm["ms_dev"] * 1e-3), unit="events/s", ms_per_step=mm["ms_dev"] / x["steps"],
                                  e2e=mm["ev_e2e"] / (mm["ms_e2e"] * 1e-3), kernel_ms=mm["adv_ms"], hbm_fraction=rf["frac"], real_fraction=mm["real_fraction"],
-                                 mean_energy_eV=mm["mean_energy"]))
+                                 real_collisions_per_s=mm["real_fraction"] * mm["ev_dev"] / (mm["ms_dev"] * 1e-3), mean_energy_eV=mm["mean_energy"], fast_mode=x.get("fast", False)))
     if rank == 0:
         traffic, fp64 = None, None
         try:   # DRAM bytes and FP64 operations of one K1 launch from an ncu capture of THESE sources (tools/capture_traffic.py); stale captures are ignored
