@@ -155,7 +155,29 @@ def run_reference_arm(args):
                             sync_factor=1.0, intervals=n_int, mean_energy_eV=mean_e),
                 cpu_baseline=dict(value=value, unit="events/s", cores=cores, kind=kind, sample=sample),
                 e2e=dict(value=value, unit="events/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
-    print(json.dumps(line))
+    emit(line)
+
+
+_JSON_FD = None
+
+
+def claim_stdout():
+    """stdout carries exactly ONE JSON line: from here on file descriptor 1 points at stderr for everything else this process and its libraries
+    print (NCCL's version banner at NCCL_DEBUG=VERSION ignores NCCL_DEBUG_FILE; the C++ front end uses printf), and emit() owns the real stdout"""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    sys.stdout.flush()
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        os.write(1, data)
+    else:
+        os.write(_JSON_FD, data)
 
 
 class StdoutToStderr:
@@ -403,8 +425,9 @@ def main():
     ap.add_argument("--t3s-setup", default="default", choices=["default", "fixture"])
     ap.add_argument("--fast-mode", action="store_true", help="with --time-to-3sigma: numericsMC.fastMode: true")
     args = ap.parse_args()
+    claim_stdout()
     if args.time_to_3sigma:
-        print(json.dumps(run_time_to_3sigma(args.t3s_setup, with_reference=True, fast_mode=args.fast_mode)))
+        emit(run_time_to_3sigma(args.t3s_setup, with_reference=True, fast_mode=args.fast_mode))
         return
     if args.warmup < 3:
         args.warmup = 3
@@ -499,7 +522,7 @@ def main():
                                                            events=fm["events"], note="numericsMC.fastMode: true (per-energy-band trial frequencies; not a reference key)")
             except Exception as ex:
                 line["time_to_3sigma"] = dict(value=None, error=str(ex))
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -6,6 +6,8 @@
 // when no CUDA device is usable.
 #include "../../include/lokib200.h"
 
+#include <atomic>
+#include <chrono>
 #include <dlfcn.h>
 #include <nccl.h>
 
@@ -28,7 +30,7 @@ static_assert(LOKIB200_R_N_REAL == R_N_REAL && LOKIB200_R_GROWTH == R_GROWTH && 
               "result layout");
 static_assert(sizeof(lokib200_electron) == sizeof(ElectronIO) && sizeof(lokib200_event_out) == sizeof(EventIO), "parity structs");
 
-static std::string g_create_error;
+static thread_local std::string g_create_error;   // engines are driven from several host threads (concurrent jobs of a sweep)
 
 struct lokib200_engine {
   lokib200_config cfg{};
@@ -98,9 +100,29 @@ struct lokib200_engine {
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pool;
   size_t ev_used = 0;
   bool timing = true;
+
+  // the blocking interval of a small ensemble as ONE CUDA graph launch (advance_graph below): index = sample flag
+  struct IntervalGraph {
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    cudaGraphNode_t k1 = nullptr, pc_copy = nullptr, pc_lottery = nullptr;   // the nodes whose arguments change from interval to interval
+    cudaKernelNodeParams k1_p{}, copy_p{}, lot_p{};
+    int kernels = 0;
+  } ig[2];
+  bool graph_off = false;
+
+  // host-side time split of the blocking interval (LOKIB200_PROFILE=1 prints it when the engine is destroyed)
+  double prof_submit = 0, prof_wait = 0, prof_outside = 0, prof_last_return = 0;
+  int64_t prof_calls = 0;
 };
 
 namespace {
+
+void drop_graph(lokib200_engine::IntervalGraph& g) {
+  if (g.exec) cudaGraphExecDestroy(g.exec);
+  if (g.graph) cudaGraphDestroy(g.graph);
+  g = lokib200_engine::IntervalGraph{};
+}
 
 #define CK(call)                                                                                                         \
   do {                                                                                                                   \
@@ -214,7 +236,7 @@ int launch_stream_t(lokib200_engine* h, const Model& m, const AdvArgs& a, const 
   as.pad = stream_stages_nu(h->P) ? static_cast<unsigned int>(std::min(h->nE, NU_STAGE_ROWS)) : 0u;   // rows of nu_tot the kernel stages in shared memory
   // the limit belongs to the kernel and the device, not to the engine (two engines with different P share one instantiation): raise it to the
   // budget once per instantiation and device, never lower it
-  static bool attr_set[64] = {};
+  static std::atomic<bool> attr_set[64];
   if (!attr_set[h->cfg.device & 63]) {
     CK(cudaFuncSetAttribute(k_advance_stream<F, G, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(STREAM_SMEM_BUDGET)));
     CK(cudaFuncSetAttribute(k_advance_stream<F, G, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
@@ -298,15 +320,12 @@ struct NcclApi {
   std::string why;
   bool ok = false;
 };
-NcclApi* nccl_api() {
-  static NcclApi api;
-  static bool tried = false;
-  if (tried) return &api;
-  tried = true;
+NcclApi load_nccl() {
+  NcclApi api;
   void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL);
   if (!lib) lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
   if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
-  if (!lib) { api.why = std::string("cannot load libnccl.so.2: ") + dlerror(); return &api; }
+  if (!lib) { api.why = std::string("cannot load libnccl.so.2: ") + dlerror(); return api; }
   auto sym = [&](const char* n) { void* p = dlsym(lib, n); if (!p) api.why = std::string("libnccl misses ") + n; return p; };
   api.GetUniqueId = reinterpret_cast<decltype(api.GetUniqueId)>(sym("ncclGetUniqueId"));
   api.CommInitRank = reinterpret_cast<decltype(api.CommInitRank)>(sym("ncclCommInitRank"));
@@ -317,6 +336,10 @@ NcclApi* nccl_api() {
   api.GroupEnd = reinterpret_cast<decltype(api.GroupEnd)>(sym("ncclGroupEnd"));
   api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(sym("ncclGetErrorString"));
   api.ok = api.GetUniqueId && api.CommInitRank && api.CommInitAll && api.CommDestroy && api.AllReduce && api.GroupStart && api.GroupEnd && api.GetErrorString;
+  return api;
+}
+NcclApi* nccl_api() {
+  static NcclApi api = load_nccl();   // initialised once, thread-safe
   return &api;
 }
 #define NK(call)                                                                                                         \
@@ -425,14 +448,25 @@ void lokib200_destroy(lokib200_engine* h) {
   cudaSetDevice(h->cfg.device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   if (h->comm) { NcclApi* nc = nccl_api(); if (nc->ok) nc->CommDestroy(h->comm); h->comm = nullptr; }
+  for (auto& g : h->ig) drop_graph(g);
+  if (h->prof_calls > 1 && std::getenv("LOKIB200_PROFILE"))
+    std::fprintf(stderr, "lokib200 engine %p: %lld graph intervals; per interval: submit %.1f us, stream wait %.1f us, outside the call %.1f us\n", static_cast<void*>(h),
+                 static_cast<long long>(h->prof_calls), h->prof_submit / h->prof_calls, h->prof_wait / h->prof_calls, h->prof_outside / h->prof_calls);
   void* ptrs[] = {h->d_type, h->d_angular, h->d_gas_first, h->d_gas_last, h->d_ap0, h->d_ap1, h->d_mass, h->d_redmass, h->d_eloss, h->d_thstd, h->d_wpar,
                   h->d_gas_fraction, h->d_cum, h->d_nu_tot, h->d_pair, h->d_state, h->d_id, h->lists.birth, h->lists.dead, h->lists.freed, h->lists.claim, h->lists.dead_flag,
                   h->lists.growth_terms, h->lists.counters, h->pend.col, h->d_adv_part, h->d_birth_part, h->d_smp_part, h->d_result, h->d_pc_result, h->d_maxbits, h->d_eeh, h->d_eah,
                   h->d_evh, h->d_eeh_per, h->d_hist_red};
+  const bool prof = std::getenv("LOKIB200_PROFILE") != nullptr;
+  auto us = [] { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  const double t0 = us();
   for (void* p : ptrs) if (p) cudaFree(p);
+  const double t1 = us();
   if (h->h_result) cudaFreeHost(h->h_result);
+  const double t2 = us();
   for (auto& pr : h->ev_pool) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
+  const double t3 = us();
   if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+  if (prof) std::fprintf(stderr, "lokib200 engine %p released: device memory %.0f us, pinned memory %.0f us, %zu events %.0f us, stream %.0f us\n", static_cast<void*>(h), t1 - t0, t2 - t1, 2 * h->ev_pool.size(), t3 - t2, us() - t3);
   delete h;
 }
 
@@ -486,6 +520,7 @@ int lokib200_set_processes(lokib200_engine* h, const lokib200_process_soa* p) {
   h->use_tile = h->cfg.n_electrons >= static_cast<int64_t>(4) * POOL * 2 * h->sm_count;
   if (const char* env = std::getenv("LOKIB200_KERNEL")) { if (!std::strcmp(env, "thread")) h->use_tile = false; else if (!std::strcmp(env, "stream") || !std::strcmp(env, "tile")) h->use_tile = true; }
   if (stream_smem_bytes(P) > STREAM_SMEM_BUDGET) h->use_tile = false;   // more than half an SM's shared memory: fall back to one electron per thread
+  for (auto& g : h->ig) drop_graph(g);   // the captured launches hold the buffers released below
   for (double** q : {&h->d_adv_part, &h->d_birth_part, &h->d_smp_part, &h->d_result}) if (*q) { cudaFree(*q); *q = nullptr; }
   if (h->h_result) { cudaFreeHost(h->h_result); h->h_result = nullptr; }
   CK(cudaMalloc(&h->d_adv_part, static_cast<size_t>(std::max(h->adv_blocks, h->tile_blocks)) * h->part_len * sizeof(double)));
@@ -676,21 +711,22 @@ int lokib200_get_ensemble(lokib200_engine* h, double* soa8) {
 
 double lokib200_time(const lokib200_engine* h) { return h ? h->time : LOKIB200_NON_DEF; }
 
-int lokib200_advance_to_sync_device(lokib200_engine* h, double nu_trial, double t_sync, int32_t sample, double* d_result) {
-  int rc = ensure_ready(h, true);
-  if (rc) return rc;
-  if (!(nu_trial > 0) || !(t_sync > h->time)) return fail(h, LOKIB200_ERR_INVALID, "need nu_trial > 0 and t_sync > current time");
-  CK(cudaSetDevice(h->cfg.device));
-  if (h->fast_mode && (h->band_for_nu != nu_trial || h->band_for_version != h->table_version)) build_bands(h, nu_trial);
-  const Model m = make_model(h);
-  ++h->interval;
-  AdvArgs a{};
-  a.n = h->cfg.n_electrons; a.first_id = h->cfg.first_electron_id; a.seed = h->cfg.seed; a.interval = h->interval;
-  a.nu_trial = nu_trial; a.t0 = h->time; a.t_sync = t_sync;
+// node added to a capturing stream by the launch just made (null outside a capture)
+static cudaGraphNode_t last_captured_node(cudaStream_t stream) {
+  cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+  const cudaGraphNode_t* deps = nullptr;
+  size_t nd = 0;
+  if (cudaStreamGetCaptureInfo(stream, &st, nullptr, nullptr, &deps, &nd) != cudaSuccess || st != cudaStreamCaptureStatusActive || nd != 1) return nullptr;
+  return deps[0];
+}
+
+// everything one synchronisation interval launches, in stream order; `tap` (capture only) receives the nodes with per-interval arguments
+static int enqueue_interval(lokib200_engine* h, const Model& m, const AdvArgs& a, bool sample, double* d_result, lokib200_engine::IntervalGraph* tap) {
+  int rc = 0;
   const bool fused = sample && !h->has_pc;
   HistGrid no_hist{};   // histograms are sampled by lokib200_sample_histograms
   cudaEvent_t e0 = nullptr, e1 = nullptr;
-  const bool timed = h->timing && h->ev_used < lokib200_engine::EV_CAP;
+  const bool timed = !tap && h->timing && h->ev_used < lokib200_engine::EV_CAP;
   if (timed) {
     if (h->ev_used == h->ev_pool.size()) {
       cudaEvent_t a0, a1; CK(cudaEventCreate(&a0)); CK(cudaEventCreate(&a1));
@@ -699,47 +735,148 @@ int lokib200_advance_to_sync_device(lokib200_engine* h, double nu_trial, double 
     e0 = h->ev_pool[h->ev_used].first; e1 = h->ev_pool[h->ev_used].second; ++h->ev_used;
     CK(cudaEventRecord(e0, h->stream));
   }
+  int kernels = 0;
   if (h->use_tile) { if ((rc = launch_stream(h, m, a, no_hist))) return rc; h->last_adv_blocks = h->tile_blocks; h->permuted = true; }
   else { if ((rc = launch_advance(h, fused, m, a, no_hist))) return rc; h->last_adv_blocks = h->adv_blocks; }
+  if (tap) tap->k1 = last_captured_node(h->stream);
   if (timed) CK(cudaEventRecord(e1, h->stream));
-  ++h->launches;
+  ++kernels;
   CK(cudaGetLastError());
   const double* smp = nullptr;
   const double* births = nullptr;
-  if (h->has_pc && h->use_tile) { launch_births(h, m, a); ++h->launches; births = h->d_birth_part; CK(cudaGetLastError()); }
+  if (h->has_pc && h->use_tile) { launch_births(h, m, a); ++kernels; births = h->d_birth_part; CK(cudaGetLastError()); }
   if (h->has_pc) {
     const int pcb = std::max(1, std::min(h->sm_count * 2, static_cast<int>((h->lists.birth_cap + 255) / 256)));
     k_pc_fill<<<pcb, 256, 0, h->stream>>>(h->st, h->lists);
     k_pc_copy<<<pcb, 256, 0, h->stream>>>(h->st, h->lists, a.n, a.first_id, a.seed, a.interval);
+    if (tap) tap->pc_copy = last_captured_node(h->stream);
     k_pc_lottery<<<pcb, 256, 0, h->stream>>>(h->st, h->lists, a.n, a.first_id, a.seed, a.interval);
+    if (tap) tap->pc_lottery = last_captured_node(h->stream);
     k_pc_place<<<pcb, 256, 0, h->stream>>>(h->st, h->lists, a.n);
     k_pc_reset<<<1, 256, 0, h->stream>>>(h->lists, a.n, h->d_pc_result);
-    h->launches += 5;
+    kernels += 5;
   }
   if (sample && (h->has_pc || h->use_tile)) {   // separate sampling pass (the thread kernel fuses it when nothing can be born or lost)
     k_sample<<<h->smp_blocks, ADV_THREADS, 16, h->stream>>>(h->st, a.n, no_hist, h->P, h->d_smp_part);
-    ++h->launches;
+    ++kernels;
     smp = h->d_smp_part;
   }
   k_finalize<<<h->part_len, 32, 0, h->stream>>>(h->d_adv_part, h->last_adv_blocks, births, h->birth_blocks, smp, h->smp_blocks,
                                                 h->has_pc ? h->d_pc_result : nullptr, h->P, d_result ? d_result : h->d_result);
-  ++h->launches;
+  ++kernels;
   CK(cudaGetLastError());
+  if (tap) tap->kernels = kernels; else h->launches += kernels;
+  return 0;
+}
+
+static int begin_interval(lokib200_engine* h, double nu_trial, double t_sync, Model& m, AdvArgs& a) {
+  int rc = ensure_ready(h, true);
+  if (rc) return rc;
+  if (!(nu_trial > 0) || !(t_sync > h->time)) return fail(h, LOKIB200_ERR_INVALID, "need nu_trial > 0 and t_sync > current time");
+  CK(cudaSetDevice(h->cfg.device));
+  if (h->fast_mode && (h->band_for_nu != nu_trial || h->band_for_version != h->table_version)) build_bands(h, nu_trial);
+  m = make_model(h);
+  ++h->interval;
+  a = AdvArgs{};
+  a.n = h->cfg.n_electrons; a.first_id = h->cfg.first_electron_id; a.seed = h->cfg.seed; a.interval = h->interval;
+  a.nu_trial = nu_trial; a.t0 = h->time; a.t_sync = t_sync;
+  return 0;
+}
+
+int lokib200_advance_to_sync_device(lokib200_engine* h, double nu_trial, double t_sync, int32_t sample, double* d_result) {
+  Model m; AdvArgs a;
+  int rc = begin_interval(h, nu_trial, t_sync, m, a);
+  if (rc) return rc;
+  if ((rc = enqueue_interval(h, m, a, sample != 0, d_result, nullptr))) return rc;
   h->time = t_sync;
   return 0;
 }
 
-int lokib200_read_result(lokib200_engine* h, double* result) {
-  if (!h || !h->d_result) return LOKIB200_ERR_INVALID;
+static int enqueue_result_copy(lokib200_engine* h) {
   CK(cudaSetDevice(h->cfg.device));
   CK(cudaMemcpyAsync(h->h_result, h->d_result, h->part_len * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  return 0;
+}
+static int wait_result(lokib200_engine* h, double* result) {
   CK(cudaStreamSynchronize(h->stream));
   if (result) std::memcpy(result, h->h_result, h->part_len * sizeof(double));
   if (h->h_result[R_OVERFLOW] != 0) return fail(h, LOKIB200_ERR_OVERFLOW, "birth/death list overflow inside one synchronisation interval (on this or another rank)");
   return 0;
 }
 
+int lokib200_read_result(lokib200_engine* h, double* result) {
+  if (!h || !h->d_result) return LOKIB200_ERR_INVALID;
+  const int rc = enqueue_result_copy(h);
+  return rc ? rc : wait_result(h, result);
+}
+
+// The blocking interval of a small ensemble (one electron per thread: K1, five population-control kernels, k_sample, k_finalize, the copy of
+// the result vector) is a chain of ~10 short launches: as separate API calls they cost more host time than device time, and they serialise the
+// host threads of jobs that run side by side (host/run.cpp).  It is captured ONCE per engine as a CUDA graph; every interval then costs the
+// argument update of the nodes that see the interval (K1: model + interval arguments; the two lottery kernels: the interval number), one graph
+// launch and one stream wait.  Same kernels, same arguments, same order: results are those of the plain launches (LOKIB200_GRAPH=0 selects them).
+static bool graph_eligible(lokib200_engine* h) {
+  if (h->graph_off || h->use_tile || h->comm) return false;
+  static const bool env_off = [] { const char* e = std::getenv("LOKIB200_GRAPH"); return e && e[0] == '0'; }();
+  return !env_off;
+}
+
+static double now_us() { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
+static int advance_graph(lokib200_engine* h, double nu_trial, double t_sync, bool sample, double* result) {
+  const double t_in = now_us();
+  Model m; AdvArgs a;
+  int rc = begin_interval(h, nu_trial, t_sync, m, a);
+  if (rc) return rc;
+  lokib200_engine::IntervalGraph& g = h->ig[sample ? 1 : 0];
+  if (!g.exec) {
+    bool ok = cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+    if (ok) {
+      ok = enqueue_interval(h, m, a, sample, nullptr, &g) == 0 &&
+           cudaMemcpyAsync(h->h_result, h->d_result, h->part_len * sizeof(double), cudaMemcpyDeviceToHost, h->stream) == cudaSuccess;
+      ok = (cudaStreamEndCapture(h->stream, &g.graph) == cudaSuccess) && ok && g.graph && g.k1 && (!h->has_pc || (g.pc_copy && g.pc_lottery));
+    }
+    if (ok) ok = cudaGraphInstantiate(&g.exec, g.graph, 0) == cudaSuccess;
+    if (ok) ok = cudaGraphKernelNodeGetParams(g.k1, &g.k1_p) == cudaSuccess;
+    if (ok && h->has_pc) ok = cudaGraphKernelNodeGetParams(g.pc_copy, &g.copy_p) == cudaSuccess && cudaGraphKernelNodeGetParams(g.pc_lottery, &g.lot_p) == cudaSuccess;
+    if (!ok) {   // no graph on this engine: the plain launches of the same interval
+      cudaGetLastError();
+      drop_graph(g);
+      h->graph_off = true;
+      if ((rc = enqueue_interval(h, m, a, sample, nullptr, nullptr))) return rc;
+      h->time = t_sync;
+      if ((rc = enqueue_result_copy(h))) return rc;
+          return wait_result(h, result);
+    }
+  } else {
+    HistGrid no_hist{};
+    double* part = h->d_adv_part;
+    void* k1_args[6] = {&m, &h->st, &h->lists, &a, &no_hist, &part};
+    cudaKernelNodeParams p = g.k1_p;
+    p.kernelParams = k1_args; p.extra = nullptr;
+    CK(cudaGraphExecKernelNodeSetParams(g.exec, g.k1, &p));
+    if (h->has_pc) {
+      void* pc_args[6] = {&h->st, &h->lists, &a.n, &a.first_id, &a.seed, &a.interval};
+      p = g.copy_p; p.kernelParams = pc_args; p.extra = nullptr;
+      CK(cudaGraphExecKernelNodeSetParams(g.exec, g.pc_copy, &p));
+      p = g.lot_p; p.kernelParams = pc_args; p.extra = nullptr;
+      CK(cudaGraphExecKernelNodeSetParams(g.exec, g.pc_lottery, &p));
+    }
+  }
+  CK(cudaGraphLaunch(g.exec, h->stream));
+  h->launches += g.kernels;
+  h->last_adv_blocks = h->adv_blocks;
+  h->time = t_sync;
+  const double t_submitted = now_us();
+  rc = wait_result(h, result);
+  const double t_out = now_us();
+  if (h->prof_calls++ > 0) h->prof_outside += t_in - h->prof_last_return;
+  h->prof_submit += t_submitted - t_in; h->prof_wait += t_out - t_submitted; h->prof_last_return = t_out;
+  return rc;
+}
+
 int lokib200_advance_to_sync(lokib200_engine* h, double nu_trial, double t_sync, int32_t sample, double* result) {
+  if (h && graph_eligible(h)) return advance_graph(h, nu_trial, t_sync, sample != 0, result);
   int rc = lokib200_advance_to_sync_device(h, nu_trial, t_sync, sample, nullptr);
   if (rc) return rc;
   if (h->comm) {   // shards of one job: every rank returns the combined vector
@@ -938,7 +1075,7 @@ int lokib200_sample_histograms(lokib200_engine* h, int32_t phase_index) {
   h->hist_reduced = false;
   g.eeh_phase = (phase_index >= 0) ? h->d_eeh_per + static_cast<size_t>(phase_index) * g.nEn : nullptr;
   const size_t hsmem = (static_cast<size_t>(g.nEn) + hist_tile_words(g)) * 4 + 16;
-  static bool attr_set[64] = {};
+  static std::atomic<bool> attr_set[64];
   if (!attr_set[h->cfg.device & 63]) { CK(cudaFuncSetAttribute(k_histogram, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); attr_set[h->cfg.device & 63] = true; }
   if (hsmem > 100 * 1024) return fail(h, LOKIB200_ERR_INVALID, "histogram grids too fine for the shared-memory tiles");
   const int hblocks = static_cast<int>(std::min<int64_t>((h->cfg.n_electrons + HIST_THREADS - 1) / HIST_THREADS, static_cast<int64_t>(h->sm_count) * 2));

@@ -149,6 +149,10 @@ struct lokib200_job {
     return 0;
   }
   int advance(double tSync, bool sample) {
+    if (engines.size() == 1 && !useComm) {   // the blocking call: for a small ensemble the whole interval is one CUDA graph launch (csrc/lokib200.cu, advance_graph)
+      int rc = lokib200_advance_to_sync(engines[0], trialCollisionFrequency, tSync, sample ? 1 : 0, res.data());
+      return rc ? engineFail(engines[0], rc) : 0;
+    }
     // (the launches are asynchronous: all GPUs run concurrently; collect() waits for them)
     for (auto* e : engines) { int rc = lokib200_advance_to_sync_device(e, trialCollisionFrequency, tSync, sample ? 1 : 0, nullptr); if (rc) return engineFail(e, rc); }
     return collect();

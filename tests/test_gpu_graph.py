@@ -1,0 +1,66 @@
+"""The blocking interval of a small ensemble is one CUDA graph launch (csrc/lokib200.cu, advance_graph): same kernels, same arguments, same
+order as the plain launches of lokib200_advance_to_sync_device + lokib200_read_result, so the result vectors and the ensembles must be
+IDENTICAL -- across table rebuilds, trial-frequency changes, fast mode, and with/without the sampling pass."""
+import numpy as np
+import pytest
+
+import golden_io as gio
+import test_gpu_parity as T
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("name,fast", [("reid_dc", 0), ("o2_sdcs", 0), ("n2_true_acb", 0), ("arhe", 0), ("n2_aniso", 1), ("ls_att_aniso", 0)])
+def test_graph_interval_equals_plain_launches(name, fast):
+    g = gio.load(name)
+    n = 30_000
+    hot = name in ("arhe", "o2_sdcs", "ls_att_aniso")
+    s0 = T._start_state(g, n, np.random.default_rng(8), 1e-2, 30.0 if hot else 5.0)
+    out = []
+    for graph in (True, False):
+        eng = T._engine(g, n, seed=4242)
+        assert eng.kernel_form() == "k_advance"
+        if fast:
+            eng.set_fast_mode(True)
+        eng.build_tables(60.0 if hot else 12.0)
+        nu = eng.table_info()["nu_max_last"]
+        eng.set_ensemble(s0, 0.0)
+        res, t = [], 0.0
+        for it in range(1, 13):
+            if it == 5:       # a table rebuild and a new trial frequency in the middle of the run
+                eng.build_tables(90.0 if hot else 20.0)
+                nu = 1.07 * eng.table_info()["nu_max_last"]
+            t += 1.0 / nu
+            sample = it % 4 != 0      # both graphs of the engine: with and without the sampling pass
+            if graph:
+                res.append(eng.advance(nu, t, sample=sample))
+            else:
+                eng.advance_device(nu, t, sample, None)
+                res.append(eng.read_result())
+        out.append((res, eng.get_ensemble(), eng.launch_count()))
+        eng.close()
+    import loki_mc_b200 as lk
+    R = lk.R
+    (ra, ea, la), (rb, eb, lb) = out
+    assert la == lb       # the graph launches exactly the kernels of the plain path
+    exact = True
+    for it, (a, b) in enumerate(zip(ra, rb)):
+        # after the first birth / attachment the lottery's equally likely victims depend on an atomic list order: from the
+        # sampling pass of that interval on, the two runs are two realisations of the same ensemble
+        events = a[R.N_REAL] + a[R.N_NULL]
+        if exact:
+            for j in (R.N_REAL, R.N_NULL, R.N_BORN, R.N_ATTACHED):
+                assert a[j] == b[j], (it, j)
+            assert np.array_equal(a[R.HEADER:], b[R.HEADER:]), it        # per-process counts and energy tallies of the interval's events
+        if a[R.N_BORN] + a[R.N_ATTACHED] > 0:
+            exact = False
+        if exact:
+            assert np.array_equal(a, b), (it, np.flatnonzero(a != b)[:8])
+        else:
+            assert abs(events - b[R.N_REAL] - b[R.N_NULL]) <= 0.02 * events
+            if a[R.N_SAMPLED] > 0:
+                assert a[R.N_SAMPLED] == b[R.N_SAMPLED] and abs(a[R.SUM_EPS] - b[R.SUM_EPS]) <= 0.02 * a[R.SUM_EPS]
+    if exact:
+        assert np.array_equal(ea, eb)
+    if name in ("reid_dc", "n2_true_acb", "n2_aniso"):
+        assert exact      # these ensembles stay below every ionization threshold: the comparison above was bit for bit throughout
