@@ -255,7 +255,10 @@ def run_time_to_3sigma(which="default", with_reference=True, fast_mode=False):
                 worst, worst_key = dev, "%s: %s = %.6g vs %.6g (sigma_eff %.2g)" % (sub, key, mine[key], mean, rel * abs(mean))
             checked += 1
     line = dict(metric="time_to_3sigma_s", value=wall, unit="s", higher_is_better=False, n_gpus=1, data="reference input files" if which == "default" else "synthetic fixture gases",
-                config=dict(workload=workload, fast_mode=bool(fast_mode)), within_3sigma=bool(worst <= 3.0), worst_deviation_sigma=worst, worst_parameter=worst_key, parameters_checked=checked, events=events,
+                config=dict(workload=workload, fast_mode=bool(fast_mode),
+                            schedule="the jobs of the sweep side by side on the one GPU (an engine, stream and host thread each; LOKIB200_CONCURRENT_JOBS=%s), every "
+                                     "blocking interval one CUDA graph launch; reports written in job order" % os.environ.get("LOKIB200_CONCURRENT_JOBS", "auto")),
+                within_3sigma=bool(worst <= 3.0), worst_deviation_sigma=worst, worst_parameter=worst_key, parameters_checked=checked, events=events,
                 events_per_s=events / wall)
     if which == "default":
         line["reference_recorded"] = dict(value=float(np.mean(gj["wall"])), unit="s", cores=gj["threads"], kind="reference",

@@ -105,11 +105,16 @@ struct lokib200_engine {
   struct IntervalGraph {
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t exec = nullptr;
-    cudaGraphNode_t k1 = nullptr, pc_copy = nullptr, pc_lottery = nullptr;   // the nodes whose arguments change from interval to interval
-    cudaKernelNodeParams k1_p{}, copy_p{}, lot_p{};
+    cudaGraphNode_t k1 = nullptr, pc_copy = nullptr, pc_lottery = nullptr, hist = nullptr;   // the nodes whose arguments change from interval to interval
+    cudaKernelNodeParams k1_p{}, copy_p{}, lot_p{}, hist_p{};
     int kernels = 0;
-  } ig[2];
+  } ig[4];   // index = sample flag + 2 * (the deferred histogram pass of the previous sample comes first)
   bool graph_off = false;
+  // lokib200_sample_histograms of a graph-driven engine is DEFERRED: the pass reads the ensemble, which nothing touches before the next interval,
+  // so it becomes the first node of that interval's graph (one launch less per sample); every call that reads the histograms, changes their
+  // grid or changes the ensemble by another route flushes it first (flush_pending_hist)
+  bool hist_pending = false;
+  int hist_pending_phase = -1;
 
   // host-side time split of the blocking interval (LOKIB200_PROFILE=1 prints it when the engine is destroyed)
   double prof_submit = 0, prof_wait = 0, prof_outside = 0, prof_last_return = 0;
@@ -396,6 +401,7 @@ int push_tables(lokib200_engine* h) {   // h_cum (padded) / h_nu_tot -> device
 extern "C" {
 
 static void build_bands(lokib200_engine* h, double nu_trial);
+static int flush_pending_hist(lokib200_engine* h);
 
 int lokib200_abi_version(void) { return LOKIB200_ABI_VERSION; }
 
@@ -472,6 +478,7 @@ void lokib200_destroy(lokib200_engine* h) {
 
 int lokib200_set_stream(lokib200_engine* h, void* cuda_stream) {
   if (!h) return LOKIB200_ERR_INVALID;
+  { const int frc = flush_pending_hist(h); if (frc) return frc; }
   CK(cudaSetDevice(h->cfg.device));
   if (h->stream) CK(cudaStreamSynchronize(h->stream));
   if (h->own_stream && h->stream) { cudaStreamDestroy(h->stream); h->own_stream = false; }
@@ -656,6 +663,7 @@ double lokib200_nu_max_at(const lokib200_engine* h, int32_t index) {
 int lokib200_init_ensemble(lokib200_engine* h, double temp_ratio, double* max_energy) {
   int rc = ensure_ready(h, false);
   if (rc) return rc;
+  { const int frc = flush_pending_hist(h); if (frc) return frc; }
   CK(cudaSetDevice(h->cfg.device));
   const double sd = std::sqrt(KB * temp_ratio * h->cfg.gas_temperature / ME);   // BMC.C:496
   CK(cudaMemsetAsync(h->d_maxbits, 0, sizeof(unsigned long long), h->stream));
@@ -675,6 +683,7 @@ int lokib200_init_ensemble(lokib200_engine* h, double temp_ratio, double* max_en
 
 int lokib200_set_ensemble(lokib200_engine* h, const double* soa8, double time) {
   if (!h || !soa8) return LOKIB200_ERR_INVALID;
+  { const int frc = flush_pending_hist(h); if (frc) return frc; }
   CK(cudaSetDevice(h->cfg.device));
   CK(cudaMemcpyAsync(h->d_state, soa8, 8 * static_cast<size_t>(h->cfg.n_electrons) * sizeof(double), cudaMemcpyHostToDevice, h->stream));
   const int blocks = static_cast<int>(std::min<int64_t>((h->cfg.n_electrons + 255) / 256, static_cast<int64_t>(h->sm_count) * 8));
@@ -718,6 +727,40 @@ static cudaGraphNode_t last_captured_node(cudaStream_t stream) {
   size_t nd = 0;
   if (cudaStreamGetCaptureInfo(stream, &st, nullptr, nullptr, &deps, &nd) != cudaSuccess || st != cudaStreamCaptureStatusActive || nd != 1) return nullptr;
   return deps[0];
+}
+
+static bool graph_eligible(lokib200_engine* h);
+
+// launch geometry of the histogram pass for the current grid
+static void histogram_launch_shape(const lokib200_engine* h, int& blocks, size_t& smem) {
+  smem = (static_cast<size_t>(h->hist.nEn) + hist_tile_words(h->hist)) * 4 + 16;
+  blocks = static_cast<int>(std::min<int64_t>((h->cfg.n_electrons + HIST_THREADS - 1) / HIST_THREADS, static_cast<int64_t>(h->sm_count) * 2));
+}
+static HistGrid histogram_args(const lokib200_engine* h, int phase_index) {
+  HistGrid g = h->hist;
+  g.eeh_phase = (phase_index >= 0) ? h->d_eeh_per + static_cast<size_t>(phase_index) * g.nEn : nullptr;
+  return g;
+}
+
+// getTimeDependDistributions' counting pass (BMC.C:1551-1571) over the current ensemble
+static int enqueue_histograms(lokib200_engine* h, int phase_index, lokib200_engine::IntervalGraph* tap) {
+  CK(cudaSetDevice(h->cfg.device));
+  const HistGrid g = histogram_args(h, phase_index);
+  h->hist_reduced = false;
+  int hblocks; size_t hsmem;
+  histogram_launch_shape(h, hblocks, hsmem);
+  static std::atomic<bool> attr_set[64];
+  if (!attr_set[h->cfg.device & 63]) { CK(cudaFuncSetAttribute(k_histogram, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); attr_set[h->cfg.device & 63] = true; }
+  if (hsmem > 100 * 1024) return fail(h, LOKIB200_ERR_INVALID, "histogram grids too fine for the shared-memory tiles");
+  k_histogram<<<hblocks, HIST_THREADS, hsmem, h->stream>>>(h->st, h->cfg.n_electrons, g);
+  if (tap) tap->hist = last_captured_node(h->stream); else ++h->launches;
+  CK(cudaGetLastError());
+  return 0;
+}
+static int flush_pending_hist(lokib200_engine* h) {
+  if (!h || !h->hist_pending) return 0;
+  h->hist_pending = false;
+  return enqueue_histograms(h, h->hist_pending_phase, nullptr);
 }
 
 // everything one synchronisation interval launches, in stream order; `tap` (capture only) receives the nodes with per-interval arguments
@@ -785,6 +828,7 @@ static int begin_interval(lokib200_engine* h, double nu_trial, double t_sync, Mo
 
 int lokib200_advance_to_sync_device(lokib200_engine* h, double nu_trial, double t_sync, int32_t sample, double* d_result) {
   Model m; AdvArgs a;
+  { const int frc = flush_pending_hist(h); if (frc) return frc; }
   int rc = begin_interval(h, nu_trial, t_sync, m, a);
   if (rc) return rc;
   if ((rc = enqueue_interval(h, m, a, sample != 0, d_result, nullptr))) return rc;
@@ -828,25 +872,31 @@ static int advance_graph(lokib200_engine* h, double nu_trial, double t_sync, boo
   Model m; AdvArgs a;
   int rc = begin_interval(h, nu_trial, t_sync, m, a);
   if (rc) return rc;
-  lokib200_engine::IntervalGraph& g = h->ig[sample ? 1 : 0];
+  const bool with_hist = h->hist_pending;
+  const int hist_phase = h->hist_pending_phase;
+  h->hist_pending = false;
+  lokib200_engine::IntervalGraph& g = h->ig[(sample ? 1 : 0) + (with_hist ? 2 : 0)];
   if (!g.exec) {
     bool ok = cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
     if (ok) {
-      ok = enqueue_interval(h, m, a, sample, nullptr, &g) == 0 &&
+      ok = (!with_hist || enqueue_histograms(h, hist_phase, &g) == 0) && enqueue_interval(h, m, a, sample, nullptr, &g) == 0 &&
            cudaMemcpyAsync(h->h_result, h->d_result, h->part_len * sizeof(double), cudaMemcpyDeviceToHost, h->stream) == cudaSuccess;
-      ok = (cudaStreamEndCapture(h->stream, &g.graph) == cudaSuccess) && ok && g.graph && g.k1 && (!h->has_pc || (g.pc_copy && g.pc_lottery));
+      ok = (cudaStreamEndCapture(h->stream, &g.graph) == cudaSuccess) && ok && g.graph && g.k1 && (!h->has_pc || (g.pc_copy && g.pc_lottery)) && (!with_hist || g.hist);
     }
     if (ok) ok = cudaGraphInstantiate(&g.exec, g.graph, 0) == cudaSuccess;
     if (ok) ok = cudaGraphKernelNodeGetParams(g.k1, &g.k1_p) == cudaSuccess;
     if (ok && h->has_pc) ok = cudaGraphKernelNodeGetParams(g.pc_copy, &g.copy_p) == cudaSuccess && cudaGraphKernelNodeGetParams(g.pc_lottery, &g.lot_p) == cudaSuccess;
+    if (ok && with_hist) ok = cudaGraphKernelNodeGetParams(g.hist, &g.hist_p) == cudaSuccess;
+    if (ok && with_hist) ++g.kernels;
     if (!ok) {   // no graph on this engine: the plain launches of the same interval
       cudaGetLastError();
       drop_graph(g);
       h->graph_off = true;
+      if (with_hist && (rc = enqueue_histograms(h, hist_phase, nullptr))) return rc;
       if ((rc = enqueue_interval(h, m, a, sample, nullptr, nullptr))) return rc;
       h->time = t_sync;
       if ((rc = enqueue_result_copy(h))) return rc;
-          return wait_result(h, result);
+      return wait_result(h, result);
     }
   } else {
     HistGrid no_hist{};
@@ -861,6 +911,18 @@ static int advance_graph(lokib200_engine* h, double nu_trial, double t_sync, boo
       CK(cudaGraphExecKernelNodeSetParams(g.exec, g.pc_copy, &p));
       p = g.lot_p; p.kernelParams = pc_args; p.extra = nullptr;
       CK(cudaGraphExecKernelNodeSetParams(g.exec, g.pc_lottery, &p));
+    }
+    if (with_hist) {   // phase row (AC fields) and, after a regrid, the grid itself
+      HistGrid hg = histogram_args(h, hist_phase);
+      int hblocks; size_t hsmem;
+      histogram_launch_shape(h, hblocks, hsmem);
+      if (hsmem > 100 * 1024) return fail(h, LOKIB200_ERR_INVALID, "histogram grids too fine for the shared-memory tiles");
+      long long n_el = h->cfg.n_electrons;
+      void* h_args[3] = {&h->st, &n_el, &hg};
+      p = g.hist_p; p.kernelParams = h_args; p.extra = nullptr;
+      p.gridDim = dim3(static_cast<unsigned>(hblocks)); p.sharedMemBytes = static_cast<unsigned>(hsmem);
+      CK(cudaGraphExecKernelNodeSetParams(g.exec, g.hist, &p));
+      h->hist_reduced = false;
     }
   }
   CK(cudaGraphLaunch(g.exec, h->stream));
@@ -968,6 +1030,7 @@ int lokib200_comm_allreduce_histograms(lokib200_engine* const* engines, int32_t 
   NcclApi* nc = nccl_api();
   if (!nc->ok) return fail(h, LOKIB200_ERR_CUDA, nc->why);
   for (int i = 0; i < n; ++i) if (!engines[i] || !engines[i]->comm || !engines[i]->hist.enabled) return fail(h, LOKIB200_ERR_INVALID, "engine without a communicator / histogram grid");
+  for (int i = 0; i < n; ++i) { const int frc = flush_pending_hist(engines[i]); if (frc) return frc; }
   for (int i = 0; i < n; ++i) {
     lokib200_engine* e = engines[i];
     if (!e->d_hist_red) {
@@ -1019,6 +1082,7 @@ int lokib200_sample_moments(lokib200_engine* h, double* result) {
 int lokib200_regrid_energy_histograms(lokib200_engine* h, double new_max) {
   int rc = ensure_ready(h, false);
   if (rc) return rc;
+  { const int frc = flush_pending_hist(h); if (frc) return frc; }
   if (!h->hist.enabled || !(new_max > 0)) return fail(h, LOKIB200_ERR_INVALID, "no histogram grid / bad energy");
   CK(cudaSetDevice(h->cfg.device));
   HistGrid& g = h->hist;
@@ -1035,6 +1099,7 @@ int lokib200_regrid_energy_histograms(lokib200_engine* h, double new_max) {
 int lokib200_set_histogram_grid(lokib200_engine* h, double max_eedf_energy) {
   int rc = ensure_ready(h, false);
   if (rc) return rc;
+  { const int frc = flush_pending_hist(h); if (frc) return frc; }
   if (!(max_eedf_energy > 0)) return fail(h, LOKIB200_ERR_INVALID, "max_eedf_energy must be positive");
   CK(cudaSetDevice(h->cfg.device));
   const lokib200_config& c = h->cfg;
@@ -1070,23 +1135,18 @@ int lokib200_sample_histograms(lokib200_engine* h, int32_t phase_index) {
   if (rc) return rc;
   if (!h->hist.enabled) return fail(h, LOKIB200_ERR_INVALID, "call lokib200_set_histogram_grid first");
   if (phase_index >= h->cfg.n_phases) return fail(h, LOKIB200_ERR_INVALID, "phase_index out of range");
-  CK(cudaSetDevice(h->cfg.device));
-  HistGrid g = h->hist;
-  h->hist_reduced = false;
-  g.eeh_phase = (phase_index >= 0) ? h->d_eeh_per + static_cast<size_t>(phase_index) * g.nEn : nullptr;
-  const size_t hsmem = (static_cast<size_t>(g.nEn) + hist_tile_words(g)) * 4 + 16;
-  static std::atomic<bool> attr_set[64];
-  if (!attr_set[h->cfg.device & 63]) { CK(cudaFuncSetAttribute(k_histogram, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); attr_set[h->cfg.device & 63] = true; }
-  if (hsmem > 100 * 1024) return fail(h, LOKIB200_ERR_INVALID, "histogram grids too fine for the shared-memory tiles");
-  const int hblocks = static_cast<int>(std::min<int64_t>((h->cfg.n_electrons + HIST_THREADS - 1) / HIST_THREADS, static_cast<int64_t>(h->sm_count) * 2));
-  k_histogram<<<hblocks, HIST_THREADS, hsmem, h->stream>>>(h->st, h->cfg.n_electrons, g);
-  ++h->launches;
-  CK(cudaGetLastError());
-  return 0;
+  if ((rc = flush_pending_hist(h))) return rc;      // (two samples without an interval in between)
+  static const bool defer = [] { const char* e = std::getenv("LOKIB200_DEFER_HIST"); return !(e && e[0] == '0'); }();
+  if (defer && graph_eligible(h) && h->ig[1].exec) {   // this engine advances by graph launches: the pass rides in front of the next interval
+    h->hist_pending = true; h->hist_pending_phase = phase_index;
+    return 0;
+  }
+  return enqueue_histograms(h, phase_index, nullptr);
 }
 
 int lokib200_fetch_histograms(lokib200_engine* h, double* eeh, double* eah, double* evh, double* eeh_periodic) {
   if (!h || !h->hist.enabled) return fail(h, LOKIB200_ERR_INVALID, "no histogram grid");
+  { const int frc = flush_pending_hist(h); if (frc) return frc; }
   CK(cudaSetDevice(h->cfg.device));
   const HistGrid& g = h->hist;
   const size_t ne = g.nEn, nea = ne * g.nC, nev = static_cast<size_t>(g.nR) * g.nA, nep = ne * h->cfg.n_phases;

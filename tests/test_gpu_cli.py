@@ -100,3 +100,41 @@ def test_command_line_front_end():
         r = subprocess.run([sys.executable, "-m", "loki_mc_b200", os.path.join(tmp, "bad.in")], cwd=tmp, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True,
                            timeout=300, env=dict(os.environ, PYTHONPATH=os.path.dirname(HERE)))
         assert r.returncode == 1 and "single integer >= 500" in r.stdout
+
+
+@pytest.mark.timeout(300)
+def test_jobs_side_by_side_write_what_the_sequential_loop_writes(monkeypatch):
+    """host/run.cpp solves the jobs of a small-ensemble sweep side by side (one engine, stream and host thread each) and writes their reports in
+    job order: same files, same row order in the look-up tables, same numbers within the run-to-run scatter as the sequential loop
+    (LOKIB200_CONCURRENT_JOBS=1); bit-identical files where no electron is born or lost (no atomically ordered lists)."""
+    text = open(os.path.join(FIX_INPUT, "fx", "setup_out_dc.in")).read().replace("[20,80]", "[20,40,60,80]").replace("nElectrons: 400", "nElectrons: 5000")
+    trees = []
+    with tempfile.TemporaryDirectory() as tmp:
+        path = os.path.join(tmp, "job.in")
+        with open(path, "w") as f:
+            f.write(text)
+        for mode, k in (("seq", "1"), ("side", "4")):
+            monkeypatch.setenv("LOKIB200_CONCURRENT_JOBS", k)
+            summary = lk.run_setup(FIX_INPUT, path, os.path.join(tmp, mode), verbose=False)
+            assert summary.n_jobs == 4
+            files = {}
+            for dirpath, _, names in os.walk(os.path.join(tmp, mode)):
+                for name in names:
+                    files[os.path.relpath(os.path.join(dirpath, name), os.path.join(tmp, mode))] = open(os.path.join(dirpath, name), errors="replace").read()
+            trees.append(files)
+    a, b = trees
+    assert sorted(a) == sorted(b) and len(a) >= 4 * 9
+    for name in a:
+        la, lb = a[name].split("\n"), b[name].split("\n")
+        assert len(la) == len(lb) or "MCTemporalInfo" in name, name
+        if "lookUpTable" in name:       # one row per job, in job order: the first column is the swept reduced field
+            col = lambda lines: [float(NUM.findall(x)[0]) for x in lines if NUM.findall(x) and not re.search(r"[A-Za-z]{3}", x)]
+            assert col(la) == col(lb) == sorted(col(la)) and len(col(la)) == 4, name
+        if name.endswith("swarmParameters.txt"):     # (the fixture attaches electrons: population control makes the two runs two realisations)
+            checked = 0
+            for x, y in zip(la, lb):
+                if "Reduced mobility coefficient" in x or "Mean energy" in x:
+                    p, q = float(NUM.findall(x)[0]), float(NUM.findall(y)[0])
+                    assert abs(p - q) <= 0.15 * abs(q), (name, x, y)
+                    checked += 1
+            assert checked >= 2, name
