@@ -105,8 +105,8 @@ struct lokib200_engine {
   struct IntervalGraph {
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t exec = nullptr;
-    cudaGraphNode_t k1 = nullptr, pc_copy = nullptr, pc_lottery = nullptr, hist = nullptr;   // the nodes whose arguments change from interval to interval
-    cudaKernelNodeParams k1_p{}, copy_p{}, lot_p{}, hist_p{};
+    cudaGraphNode_t k1 = nullptr, births = nullptr, pc_copy = nullptr, pc_lottery = nullptr, hist = nullptr;   // the nodes whose arguments change from interval to interval
+    cudaKernelNodeParams k1_p{}, births_p{}, copy_p{}, lot_p{}, hist_p{};
     int kernels = 0;
   } ig[4];   // index = sample flag + 2 * (the deferred histogram pass of the previous sample comes first)
   bool graph_off = false;
@@ -456,7 +456,7 @@ void lokib200_destroy(lokib200_engine* h) {
   if (h->comm) { NcclApi* nc = nccl_api(); if (nc->ok) nc->CommDestroy(h->comm); h->comm = nullptr; }
   for (auto& g : h->ig) drop_graph(g);
   if (h->prof_calls > 1 && std::getenv("LOKIB200_PROFILE"))
-    std::fprintf(stderr, "lokib200 engine %p: %lld graph intervals; per interval: submit %.1f us, stream wait %.1f us, outside the call %.1f us\n", static_cast<void*>(h),
+    std::fprintf(stderr, "lokib200 engine %p: %lld blocking intervals; per interval: submit %.1f us, stream wait %.1f us, outside the call %.1f us\n", static_cast<void*>(h),
                  static_cast<long long>(h->prof_calls), h->prof_submit / h->prof_calls, h->prof_wait / h->prof_calls, h->prof_outside / h->prof_calls);
   void* ptrs[] = {h->d_type, h->d_angular, h->d_gas_first, h->d_gas_last, h->d_ap0, h->d_ap1, h->d_mass, h->d_redmass, h->d_eloss, h->d_thstd, h->d_wpar,
                   h->d_gas_fraction, h->d_cum, h->d_nu_tot, h->d_pair, h->d_state, h->d_id, h->lists.birth, h->lists.dead, h->lists.freed, h->lists.claim, h->lists.dead_flag,
@@ -787,7 +787,10 @@ static int enqueue_interval(lokib200_engine* h, const Model& m, const AdvArgs& a
   CK(cudaGetLastError());
   const double* smp = nullptr;
   const double* births = nullptr;
-  if (h->has_pc && h->use_tile) { launch_births(h, m, a); ++kernels; births = h->d_birth_part; CK(cudaGetLastError()); }
+  if (h->has_pc && h->use_tile) {
+    launch_births(h, m, a); ++kernels; births = h->d_birth_part; CK(cudaGetLastError());
+    if (tap) tap->births = last_captured_node(h->stream);
+  }
   if (h->has_pc) {
     const int pcb = std::max(1, std::min(h->sm_count * 2, static_cast<int>((h->lists.birth_cap + 255) / 256)));
     k_pc_fill<<<pcb, 256, 0, h->stream>>>(h->st, h->lists);
@@ -860,9 +863,9 @@ int lokib200_read_result(lokib200_engine* h, double* result) {
 // argument update of the nodes that see the interval (K1: model + interval arguments; the two lottery kernels: the interval number), one graph
 // launch and one stream wait.  Same kernels, same arguments, same order: results are those of the plain launches (LOKIB200_GRAPH=0 selects them).
 static bool graph_eligible(lokib200_engine* h) {
-  if (h->graph_off || h->use_tile || h->comm) return false;
-  static const bool env_off = [] { const char* e = std::getenv("LOKIB200_GRAPH"); return e && e[0] == '0'; }();
-  return !env_off;
+  if (h->graph_off || h->comm) return false;
+  static const int mode = [] { const char* e = std::getenv("LOKIB200_GRAPH"); return e ? std::atoi(e) : 1; }();   // 0 = never, 1 = one-electron-per-thread form, 2 = both forms
+  return mode >= 2 || (mode == 1 && !h->use_tile);
 }
 
 static double now_us() { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
@@ -881,12 +884,14 @@ static int advance_graph(lokib200_engine* h, double nu_trial, double t_sync, boo
     if (ok) {
       ok = (!with_hist || enqueue_histograms(h, hist_phase, &g) == 0) && enqueue_interval(h, m, a, sample, nullptr, &g) == 0 &&
            cudaMemcpyAsync(h->h_result, h->d_result, h->part_len * sizeof(double), cudaMemcpyDeviceToHost, h->stream) == cudaSuccess;
-      ok = (cudaStreamEndCapture(h->stream, &g.graph) == cudaSuccess) && ok && g.graph && g.k1 && (!h->has_pc || (g.pc_copy && g.pc_lottery)) && (!with_hist || g.hist);
+      ok = (cudaStreamEndCapture(h->stream, &g.graph) == cudaSuccess) && ok && g.graph && g.k1 && (!h->has_pc || (g.pc_copy && g.pc_lottery)) && (!with_hist || g.hist) &&
+           (!(h->has_pc && h->use_tile) || g.births);
     }
     if (ok) ok = cudaGraphInstantiate(&g.exec, g.graph, 0) == cudaSuccess;
     if (ok) ok = cudaGraphKernelNodeGetParams(g.k1, &g.k1_p) == cudaSuccess;
     if (ok && h->has_pc) ok = cudaGraphKernelNodeGetParams(g.pc_copy, &g.copy_p) == cudaSuccess && cudaGraphKernelNodeGetParams(g.pc_lottery, &g.lot_p) == cudaSuccess;
     if (ok && with_hist) ok = cudaGraphKernelNodeGetParams(g.hist, &g.hist_p) == cudaSuccess;
+    if (ok && g.births) ok = cudaGraphKernelNodeGetParams(g.births, &g.births_p) == cudaSuccess;
     if (ok && with_hist) ++g.kernels;
     if (!ok) {   // no graph on this engine: the plain launches of the same interval
       cudaGetLastError();
@@ -901,10 +906,26 @@ static int advance_graph(lokib200_engine* h, double nu_trial, double t_sync, boo
   } else {
     HistGrid no_hist{};
     double* part = h->d_adv_part;
-    void* k1_args[6] = {&m, &h->st, &h->lists, &a, &no_hist, &part};
     cudaKernelNodeParams p = g.k1_p;
-    p.kernelParams = k1_args; p.extra = nullptr;
-    CK(cudaGraphExecKernelNodeSetParams(g.exec, g.k1, &p));
+    p.extra = nullptr;
+    if (h->use_tile) {   // k_advance_stream(m, {state, ids}, lists, pending, args, grid, partials): launch_stream_t
+      StateId sid{h->st, h->d_id};
+      AdvArgs as = a;
+      as.pad = stream_stages_nu(h->P) ? static_cast<unsigned int>(std::min(h->nE, NU_STAGE_ROWS)) : 0u;
+      void* k1_args[7] = {&m, &sid, &h->lists, &h->pend, &as, &no_hist, &part};
+      p.kernelParams = k1_args;
+      CK(cudaGraphExecKernelNodeSetParams(g.exec, g.k1, &p));
+      if (g.births) {
+        double* bpart = h->d_birth_part;
+        void* b_args[5] = {&m, &h->lists, &h->pend, &a, &bpart};
+        p = g.births_p; p.kernelParams = b_args; p.extra = nullptr;
+        CK(cudaGraphExecKernelNodeSetParams(g.exec, g.births, &p));
+      }
+    } else {             // k_advance(m, state, lists, args, grid, partials): launch_advance_t
+      void* k1_args[6] = {&m, &h->st, &h->lists, &a, &no_hist, &part};
+      p.kernelParams = k1_args;
+      CK(cudaGraphExecKernelNodeSetParams(g.exec, g.k1, &p));
+    }
     if (h->has_pc) {
       void* pc_args[6] = {&h->st, &h->lists, &a.n, &a.first_id, &a.seed, &a.interval};
       p = g.copy_p; p.kernelParams = pc_args; p.extra = nullptr;
@@ -927,7 +948,8 @@ static int advance_graph(lokib200_engine* h, double nu_trial, double t_sync, boo
   }
   CK(cudaGraphLaunch(g.exec, h->stream));
   h->launches += g.kernels;
-  h->last_adv_blocks = h->adv_blocks;
+  h->last_adv_blocks = h->use_tile ? h->tile_blocks : h->adv_blocks;
+  if (h->use_tile) h->permuted = true;
   h->time = t_sync;
   const double t_submitted = now_us();
   rc = wait_result(h, result);
@@ -939,6 +961,7 @@ static int advance_graph(lokib200_engine* h, double nu_trial, double t_sync, boo
 
 int lokib200_advance_to_sync(lokib200_engine* h, double nu_trial, double t_sync, int32_t sample, double* result) {
   if (h && graph_eligible(h)) return advance_graph(h, nu_trial, t_sync, sample != 0, result);
+  const double t_in = now_us();
   int rc = lokib200_advance_to_sync_device(h, nu_trial, t_sync, sample, nullptr);
   if (rc) return rc;
   if (h->comm) {   // shards of one job: every rank returns the combined vector
@@ -946,7 +969,13 @@ int lokib200_advance_to_sync(lokib200_engine* h, double nu_trial, double t_sync,
     lokib200_engine* one[1] = {h};
     if ((rc = lokib200_comm_allreduce_results(one, 1, nullptr))) return rc;
   }
-  return lokib200_read_result(h, result);
+  if ((rc = enqueue_result_copy(h))) return rc;
+  const double t_submitted = now_us();
+  rc = wait_result(h, result);
+  const double t_out = now_us();
+  if (h->prof_calls++ > 0) h->prof_outside += t_in - h->prof_last_return;
+  h->prof_submit += t_submitted - t_in; h->prof_wait += t_out - t_submitted; h->prof_last_return = t_out;
+  return rc;
 }
 
 // ---------------------------------------------------------------- multi-GPU exchange ----------------------------------------------------------------
