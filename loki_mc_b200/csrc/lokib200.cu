@@ -857,14 +857,16 @@ int lokib200_read_result(lokib200_engine* h, double* result) {
   return rc ? rc : wait_result(h, result);
 }
 
-// The blocking interval of a small ensemble (one electron per thread: K1, five population-control kernels, k_sample, k_finalize, the copy of
-// the result vector) is a chain of ~10 short launches: as separate API calls they cost more host time than device time, and they serialise the
-// host threads of jobs that run side by side (host/run.cpp).  It is captured ONCE per engine as a CUDA graph; every interval then costs the
-// argument update of the nodes that see the interval (K1: model + interval arguments; the two lottery kernels: the interval number), one graph
-// launch and one stream wait.  Same kernels, same arguments, same order: results are those of the plain launches (LOKIB200_GRAPH=0 selects them).
+// The blocking interval (lokib200_advance_to_sync: K1, the births pass of the streaming form, five population-control kernels, k_sample, k_finalize,
+// the copy of the result vector) is a chain of ~10 launches.  For a small ensemble they cost more host time than device time as separate API calls
+// and serialise the host threads of jobs that run side by side (host/run.cpp); for a large one they delay the start of K1 after the host's turn.
+// The chain is captured ONCE per engine (and per sample / deferred-histogram flag) as a CUDA graph; every interval then costs the argument update
+// of the nodes that see the interval (K1 and the births pass: model + interval arguments; the two lottery kernels: the interval number), one graph
+// launch and one stream wait.  Same kernels, same arguments, same order: results are those of the plain launches, which
+// lokib200_advance_to_sync_device keeps using.  LOKIB200_GRAPH=0 selects the plain launches here too, 1 restricts the graph to the thread form.
 static bool graph_eligible(lokib200_engine* h) {
   if (h->graph_off || h->comm) return false;
-  static const int mode = [] { const char* e = std::getenv("LOKIB200_GRAPH"); return e ? std::atoi(e) : 1; }();   // 0 = never, 1 = one-electron-per-thread form, 2 = both forms
+  static const int mode = [] { const char* e = std::getenv("LOKIB200_GRAPH"); return e ? std::atoi(e) : 2; }();   // 0 = never, 1 = one-electron-per-thread form only, 2 = both forms (default)
   return mode >= 2 || (mode == 1 && !h->use_tile);
 }
 

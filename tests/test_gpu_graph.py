@@ -10,8 +10,10 @@ import test_gpu_parity as T
 pytestmark = pytest.mark.gpu
 
 
+@pytest.mark.parametrize("kernel", ["thread", "stream"])
 @pytest.mark.parametrize("name,fast", [("reid_dc", 0), ("o2_sdcs", 0), ("n2_true_acb", 0), ("arhe", 0), ("n2_aniso", 1), ("ls_att_aniso", 0)])
-def test_graph_interval_equals_plain_launches(name, fast):
+def test_graph_interval_equals_plain_launches(name, fast, kernel, monkeypatch):
+    monkeypatch.setenv("LOKIB200_KERNEL", kernel)
     g = gio.load(name)
     n = 30_000
     hot = name in ("arhe", "o2_sdcs", "ls_att_aniso")
@@ -19,7 +21,7 @@ def test_graph_interval_equals_plain_launches(name, fast):
     out = []
     for graph in (True, False):
         eng = T._engine(g, n, seed=4242)
-        assert eng.kernel_form() == "k_advance"
+        assert eng.kernel_form() == ("k_advance" if kernel == "thread" else "k_advance_stream")
         if fast:
             eng.set_fast_mode(True)
         eng.build_tables(60.0 if hot else 12.0)
