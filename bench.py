@@ -432,11 +432,12 @@ def main():
     ap.add_argument("--no-extras", action="store_true", help="only the headline workload (skip the `also` legs and time_to_3sigma)")
     ap.add_argument("--time-to-3sigma", action="store_true", help="second metric of BASELINE.json alone: setup file in, swarm parameters out, on one GPU")
     ap.add_argument("--t3s-setup", default="default", choices=["default", "fixture"])
+    ap.add_argument("--t3s-no-reference", action="store_true", help="with --time-to-3sigma: do not run the reference beside it (its recorded time is quoted)")
     ap.add_argument("--fast-mode", action="store_true", help="with --time-to-3sigma: numericsMC.fastMode: true")
     args = ap.parse_args()
     claim_stdout()
     if args.time_to_3sigma:
-        emit(run_time_to_3sigma(args.t3s_setup, with_reference=True, fast_mode=args.fast_mode))
+        emit(run_time_to_3sigma(args.t3s_setup, with_reference=not args.t3s_no_reference, fast_mode=args.fast_mode))
         return
     if args.warmup < 3:
         args.warmup = 3
@@ -477,7 +478,7 @@ def main():
                  dict(tag="configs[1] in fast mode (per-energy-band trial frequencies, not a reference feature): fewer null events for the same physics", model=args.model, n=n,
                       S=1.0, hist=False, steps=20, fast=True),
                  dict(tag="configs[1], device-resident leg under ONE trial-frequency bound computed for the whole timed region (round-1 definition of `value`: "
-                          "a higher trial frequency, i.e. more null events per real collision)", model=args.model, n=n, S=1.0, hist=False, steps=20, long=True),
+                          "a higher trial frequency, i.e. more null events per real collision)", model=args.model, n=n, S=1.0, hist=False, steps=100, long=True),
                  dict(tag="configs[4] air, 1e9 electrons over 8 GPUs = 1.25e8 per GPU", model="air", n=125_000_000, S=1.0, hist=False, steps=10),
                  dict(tag="configs[2] Ar/He ionization growth, 1e8 electrons over 8 GPUs = 1.25e7 per GPU", model="arhe", n=12_500_000, S=1.0, hist=False, steps=20),
                  dict(tag="reference-size ensemble (1e5 electrons, configs[0] process set)", model="o2_sdcs", n=100_000, S=1.0, hist=False, steps=100)]
@@ -531,8 +532,13 @@ def main():
                 line["cpu_baseline"] = dict(value=None, unit="events/s", cores=os.cpu_count(), kind="port", sample="failed: %s" % ex)
         if world == 1 and not args.no_extras:
             try:   # BASELINE.json's second metric on configs[0], Code/Input/default_setup.in verbatim
-                line["time_to_3sigma"] = run_time_to_3sigma("default", with_reference=False)
-                fm = run_time_to_3sigma("default", with_reference=False, fast_mode=True)
+                # (its own process, as a user runs lokimc_b200: this one holds torch, the clock sampler and the OpenMP team of the CPU baseline)
+                def t3s(*extra):
+                    out = subprocess.run([sys.executable, os.path.abspath(__file__), "--time-to-3sigma", "--t3s-no-reference", *extra], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL,
+                                         text=True, timeout=900).stdout
+                    return json.loads([l for l in out.splitlines() if l.startswith("{")][-1])
+                line["time_to_3sigma"] = t3s()
+                fm = t3s("--fast-mode")
                 line["time_to_3sigma"]["fast_mode"] = dict(value=fm["value"], unit="s", within_3sigma=fm["within_3sigma"], worst_deviation_sigma=fm["worst_deviation_sigma"], worst_parameter=fm["worst_parameter"],
                                                            events=fm["events"], note="numericsMC.fastMode: true (per-energy-band trial frequencies; not a reference key)")
             except Exception as ex:

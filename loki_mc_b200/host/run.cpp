@@ -6,6 +6,7 @@
 // bound by the event chain of its slowest warp, so small jobs are solved SIDE BY SIDE, each on its own engine, stream and host thread (and, with
 // several devices, each on one device instead of sharded); their reports are written in job order, so the output folder is what the sequential
 // loop writes.  Large ensembles keep the sequential, sharded form.  LOKIB200_CONCURRENT_JOBS=k overrides the choice (1 = the sequential loop).
+#include <algorithm>
 #include <atomic>
 #include <chrono>
 #include <condition_variable>
@@ -166,7 +167,12 @@ int lokib200_run_setup(const char* input_dir, const char* setup_file, const char
     // gui.terminalDisp: MCStatus is a live display of ONE job, so it keeps the sequential loop.
     const bool status = verbose && in.controls().status_display != 0;
     int workers = 1;
-    if (nJobs > 1 && !status && in.config(0).n_electrons <= SIDE_BY_SIDE_MAX_ELECTRONS) workers = std::min(nJobs, SIDE_BY_SIDE_PER_DEVICE * n_devices);
+    if (nJobs > 1 && !status && in.config(0).n_electrons <= SIDE_BY_SIDE_MAX_ELECTRONS) {
+      // every worker spins in its stream wait: beyond about a third of the host's hardware threads they starve each other (measured: 8 workers on
+      // a 16-thread box take twice as long per interval as 5)
+      const int by_host = std::max(1, static_cast<int>(std::thread::hardware_concurrency()) / 3);
+      workers = std::max(1, std::min({nJobs, SIDE_BY_SIDE_PER_DEVICE * n_devices, by_host}));
+    }
     if (const char* env = std::getenv("LOKIB200_CONCURRENT_JOBS")) { const int k = std::atoi(env); if (k >= 1) workers = std::min(nJobs, k); }
     const bool side_by_side = workers > 1;
 
