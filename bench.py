@@ -468,6 +468,11 @@ def main():
     clocks = sampler.stop()
     fp64_peak = arm.eng.measure_fp64_peak() if rank == 0 else None
     P, L, nE = arm.P, arm.L, arm.eng.table_info()["nE"]
+    transport = arm.eng.comm_transport()
+    collective = {"none": "none (one GPU)",
+                  "peer-memory": "in-engine exchange over peer memory every interval: one kernel per GPU pushes its result vector into every peer's mailbox (NVLink stores) and adds "
+                                 "the slots in rank order (k_exchange); a graph node of the blocking call",
+                  "nccl": "in-engine grouped ncclAllReduce per interval (LOKIB200_P2P=0, or no peer access between the GPUs)"}[transport]
     arm.close()
 
     also = []
@@ -511,7 +516,7 @@ def main():
             config=dict(workload=WORKLOADS.get(args.model, args.model) + ", %.3g electrons per GPU, reference cadence (sync factor 1, ensemble sums and one combine of the shards every interval)" % n,
                         process_set=args.model, electrons_per_gpu=n, processes=P, sync_factor=1.0, relax_intervals=args.relax,
                         mean_energy_eV=m["mean_energy"], nu_trial=m["nu"], table_mib=round(nE * ((P + 15) // 16 * 16) * 8 * 3 / 2 ** 20, 1),   # cumulative table (8 B / entry) + its row-pair form (16 B / entry)
-                        l2_policy="state %.0f MB per GPU >> 126 MB L2: every step streams it from HBM" % (n * 72 / 1e6), collective="in-engine grouped ncclAllReduce per interval" if world > 1 else "none (one GPU)",
+                        l2_policy="state %.0f MB per GPU >> 126 MB L2: every step streams it from HBM" % (n * 72 / 1e6), collective=collective,
                         real_fraction=m["real_fraction"], nu_exceeded=m["nu_exceeded"], table_clamped=m["table_clamped"],
                         nu_trial_rule="the job driver's: bound of nu_tot over the energies reachable within S + 10 intervals, in both legs (the unmodified reference settles at a "
                                       "real-collision fraction of 0.31 on this point, tests/golden/ensemble_n2_aniso.json)"),

@@ -176,10 +176,13 @@ int lokib200_read_result(lokib200_engine* h, double* result);
 
 /* --- multi-GPU: the one exchange of the path ---
  * The ensemble shards by global electron id (lokib200_config.first_electron_id); tables are replicated; per sampling interval the
- * result vectors of all shards are combined by ONE grouped NCCL all-reduce (SUM entries + MAX entries) on the engines' streams, in
- * place in device memory, so that every rank holds the same combined vector and takes the same trial-frequency / table decisions.
- * Histograms are combined once per job the same way.  NCCL is loaded at run time (libnccl.so.2; the copy a host process such as
- * PyTorch has already loaded is reused).  The reference has no distributed backend (it is one OpenMP process, BMC.C:636). */
+ * result vectors of all shards are combined (SUM entries + MAX entries) in place in device memory, on the engines' streams, so that every
+ * rank holds the same combined vector and takes the same trial-frequency / table decisions.  Transport: when every GPU of the communicator
+ * can address the others (NVLink / NVSwitch peer access; CUDA IPC between processes), ONE kernel per GPU pushes its ~2.6 KB vector into a
+ * mailbox in every peer's memory and adds the n slots in rank order (k_exchange: no ring, all ranks hold the same bits); otherwise ONE
+ * grouped NCCL all-reduce.  LOKIB200_P2P=0 forces NCCL.  Histograms are combined once per job with NCCL.  NCCL is loaded at run time
+ * (libnccl.so.2; the copy a host process such as PyTorch has already loaded is reused) and also carries the 64-byte IPC handles once.
+ * The reference has no distributed backend (it is one OpenMP process, BMC.C:636). */
 #define LOKIB200_COMM_ID_BYTES 128
 int lokib200_comm_unique_id(void* id128);                                  /* ncclGetUniqueId: call on one rank, broadcast the 128 bytes */
 /* one engine per process (torchrun / mpirun): collective call on all ranks */
@@ -188,6 +191,7 @@ int lokib200_comm_init_rank(lokib200_engine* h, const void* id128, int32_t rank,
 int lokib200_comm_init_all(lokib200_engine* const* engines, int32_t n);
 int lokib200_comm_destroy(lokib200_engine* h);
 int32_t lokib200_comm_size(const lokib200_engine* h);                      /* 1 without a communicator */
+const char* lokib200_comm_transport(const lokib200_engine* h);             /* "none", "nccl" or "peer-memory": how result vectors are combined */
 /* all-reduce the result vectors the last advance / sample left on the device; `engines` are the LOCAL members of the communicator
  * (all of them after lokib200_comm_init_all, the single one after lokib200_comm_init_rank); d_results[i] may name a caller-owned
  * device vector per engine (NULL = the engine's own, which lokib200_read_result then returns).  Asynchronous on the engines' streams. */

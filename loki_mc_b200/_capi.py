@@ -149,7 +149,7 @@ SYMBOLS = ["lokib200_abi_version", "lokib200_device_count", "lokib200_create", "
            "lokib200_job_process_outputs", "lokib200_job_time_series", "lokib200_job_histograms", "lokib200_job_periodic",
            "lokib200_job_periodic_diffusion", "lokib200_job_conditions", "lokib200_job_evdf_max_speed", "lokib200_job_last_error", "lokib200_job_destroy",
            "lokib200_sample_moments_device", "lokib200_comm_unique_id", "lokib200_comm_init_rank", "lokib200_comm_init_all", "lokib200_comm_destroy",
-           "lokib200_comm_size", "lokib200_comm_allreduce_results", "lokib200_comm_allreduce_histograms", "lokib200_kernel_form", "lokib200_device_hbm_gbs", "lokib200_set_fast_mode"]
+           "lokib200_comm_size", "lokib200_comm_transport", "lokib200_comm_allreduce_results", "lokib200_comm_allreduce_histograms", "lokib200_kernel_form", "lokib200_device_hbm_gbs", "lokib200_set_fast_mode"]
 # every symbol include/lokib200_host.h declares
 HOST_SYMBOLS = ["lokib200_setup_load", "lokib200_setup_destroy", "lokib200_setup_last_error", "lokib200_setup_job_count", "lokib200_setup_job_value",
                 "lokib200_setup_variable_condition", "lokib200_setup_processes", "lokib200_setup_config", "lokib200_setup_controls",
@@ -205,6 +205,7 @@ def lib():
     L.lokib200_comm_init_all.argtypes = [C.POINTER(vp), C.c_int32]
     L.lokib200_comm_destroy.argtypes = [vp]
     L.lokib200_comm_size.argtypes = [vp]; L.lokib200_comm_size.restype = C.c_int32
+    L.lokib200_comm_transport.argtypes = [vp]; L.lokib200_comm_transport.restype = C.c_char_p
     L.lokib200_comm_allreduce_results.argtypes = [C.POINTER(vp), C.c_int32, C.POINTER(vp)]
     L.lokib200_comm_allreduce_histograms.argtypes = [C.POINTER(vp), C.c_int32]
     L.lokib200_regrid_energy_histograms.argtypes = [vp, C.c_double]
@@ -398,6 +399,10 @@ class Engine:
 
     def comm_size(self):
         return int(self.L.lokib200_comm_size(self.h))
+
+    def comm_transport(self):
+        """"none", "nccl" or "peer-memory" (lokib200_comm_transport)"""
+        return self.L.lokib200_comm_transport(self.h).decode()
 
     def comm_destroy(self):
         self._check(self.L.lokib200_comm_destroy(self.h))

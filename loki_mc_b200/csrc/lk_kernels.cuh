@@ -590,6 +590,62 @@ __global__ void k_finalize(const double* __restrict__ adv_partials, int adv_bloc
   if (lane == 0) result[j] = v;
 }
 
+// ------------------------------------------------------------------ exchange over peer memory ------------------------------------------------------------------
+// The one exchange of the path: the result vectors of the shards of a job are combined every sampling interval.  The payload is
+// ~2.6 KB, so the cost is latency, not bandwidth: one CTA per GPU pushes its vector straight into a mailbox slot in EVERY peer's memory
+// (NVLink stores), publishes a flag, waits for the flags of the others in its own mailbox and adds the n slots in rank order.  No ring, no
+// second kernel, no host: one launch per interval and GPU, and because every rank adds in the same order all ranks hold the same bits.
+// Mailbox of one rank: slot[2][n][stride] doubles, then flag[2][n] u64 (two parities: a rank can be at most one exchange ahead of another,
+// because it cannot leave exchange k + 1 before every peer has entered it, i.e. has finished reading the slots of exchange k).
+constexpr int EXCHANGE_MAX_RANKS = 16;
+constexpr int EXCHANGE_THREADS = 256;
+struct Mailboxes { double* box[EXCHANGE_MAX_RANKS]; };
+
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) { asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory"); }
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+
+__global__ void __launch_bounds__(EXCHANGE_THREADS) k_exchange(double* __restrict__ v, int len, int stride, const Mailboxes m, int me, int n, unsigned long long epoch,
+                                                               long long timeout_cycles) {
+  const int par = static_cast<int>(epoch & 1ull), tid = threadIdx.x;
+  const size_t slot_me = (static_cast<size_t>(par) * n + me) * stride, flags_at = 2ull * n * stride;
+  // 1. my vector into slot [par][me] of every rank, my own included
+  for (int r = 0; r < n; ++r) {
+    double* dst = m.box[r] + slot_me;
+    for (int j = tid; j < len; j += EXCHANGE_THREADS) dst[j] = v[j];
+  }
+  __threadfence_system();
+  __syncthreads();
+  // 2. publish: flag [par][me] of every rank <- epoch
+  if (tid < n) st_release_sys(reinterpret_cast<unsigned long long*>(m.box[tid] + flags_at) + par * n + me, epoch);
+  // 3. wait for every rank's flag in my mailbox
+  __shared__ int s_timeout;
+  if (tid == 0) s_timeout = 0;
+  __syncthreads();
+  if (tid < n) {
+    const unsigned long long* f = reinterpret_cast<const unsigned long long*>(m.box[me] + flags_at) + par * n + tid;
+    const long long t0 = clock64();
+    while (ld_acquire_sys(f) < epoch) {
+      if (clock64() - t0 > timeout_cycles) { s_timeout = 1; break; }   // a peer that never arrives must not hang the GPU
+      __nanosleep(100);
+    }
+  }
+  __syncthreads();
+  // 4. the same sum on every rank: slots in rank order; [R_SUM_COUNT, R_HEADER) by max
+  const double* mine = m.box[me] + static_cast<size_t>(par) * n * stride;
+  for (int j = tid; j < len; j += EXCHANGE_THREADS) {
+    double acc = __ldcg(mine + j);
+    const bool is_max = (j >= R_SUM_COUNT && j < R_HEADER);
+    for (int r = 1; r < n; ++r) { const double t = __ldcg(mine + static_cast<size_t>(r) * stride + j); acc = is_max ? fmax(acc, t) : acc + t; }
+    v[j] = acc;
+  }
+  __syncthreads();
+  if (tid == 0 && s_timeout) v[R_OVERFLOW] = 2.0;   // read by the host as an error (lokib200_read_result)
+}
+
 // ------------------------------------------------------------------ parity entry ------------------------------------------------------------------
 struct ElectronIO { double r[3], v[3], energy, t, t_cf, nu_e; };
 struct EventIO { int chosen, draws_used; double dE, dE_rel, gain_field, ej_r[3], ej_v[3], ej_energy; };

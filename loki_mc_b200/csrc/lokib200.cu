@@ -85,6 +85,13 @@ struct lokib200_engine {
   ncclComm_t comm = nullptr;
   int comm_size = 1, comm_rank = 0;
   bool comm_local_group = false;   // created by lokib200_comm_init_all: collectives must be issued for all local engines in one NCCL group
+  // per-interval exchange over peer memory (k_exchange, lk_kernels.cuh): this rank's mailbox, the peers' mailboxes mapped into this process
+  double* d_mail = nullptr;
+  Mailboxes mail{};
+  bool mail_ipc[EXCHANGE_MAX_RANKS] = {};   // box[r] was opened with cudaIpcOpenMemHandle
+  int mail_stride = 0;
+  unsigned long long exchange_epoch = 0;
+  bool p2p = false;
   unsigned long long* d_hist_red = nullptr;   // all-reduced copy of the four histogram arrays (the accumulators keep this rank's own counts)
   bool hist_reduced = false;                  // d_hist_red holds the combined counts of the current accumulators
 
@@ -105,8 +112,8 @@ struct lokib200_engine {
   struct IntervalGraph {
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t exec = nullptr;
-    cudaGraphNode_t k1 = nullptr, births = nullptr, pc_copy = nullptr, pc_lottery = nullptr, hist = nullptr;   // the nodes whose arguments change from interval to interval
-    cudaKernelNodeParams k1_p{}, births_p{}, copy_p{}, lot_p{}, hist_p{};
+    cudaGraphNode_t k1 = nullptr, births = nullptr, pc_copy = nullptr, pc_lottery = nullptr, hist = nullptr, exchange = nullptr;   // the nodes whose arguments change from interval to interval
+    cudaKernelNodeParams k1_p{}, births_p{}, copy_p{}, lot_p{}, hist_p{}, exchange_p{};
     int kernels = 0;
   } ig[4];   // index = sample flag + 2 * (the deferred histogram pass of the previous sample comes first)
   bool graph_off = false;
@@ -321,6 +328,7 @@ struct NcclApi {
   decltype(&ncclAllReduce) AllReduce = nullptr;
   decltype(&ncclGroupStart) GroupStart = nullptr;
   decltype(&ncclGroupEnd) GroupEnd = nullptr;
+  decltype(&ncclAllGather) AllGather = nullptr;
   decltype(&ncclGetErrorString) GetErrorString = nullptr;
   std::string why;
   bool ok = false;
@@ -339,6 +347,7 @@ NcclApi load_nccl() {
   api.AllReduce = reinterpret_cast<decltype(api.AllReduce)>(sym("ncclAllReduce"));
   api.GroupStart = reinterpret_cast<decltype(api.GroupStart)>(sym("ncclGroupStart"));
   api.GroupEnd = reinterpret_cast<decltype(api.GroupEnd)>(sym("ncclGroupEnd"));
+  api.AllGather = reinterpret_cast<decltype(api.AllGather)>(sym("ncclAllGather"));
   api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(sym("ncclGetErrorString"));
   api.ok = api.GetUniqueId && api.CommInitRank && api.CommInitAll && api.CommDestroy && api.AllReduce && api.GroupStart && api.GroupEnd && api.GetErrorString;
   return api;
@@ -402,6 +411,7 @@ extern "C" {
 
 static void build_bands(lokib200_engine* h, double nu_trial);
 static int flush_pending_hist(lokib200_engine* h);
+static void release_mailboxes(lokib200_engine* h);
 
 int lokib200_abi_version(void) { return LOKIB200_ABI_VERSION; }
 
@@ -454,6 +464,7 @@ void lokib200_destroy(lokib200_engine* h) {
   cudaSetDevice(h->cfg.device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   if (h->comm) { NcclApi* nc = nccl_api(); if (nc->ok) nc->CommDestroy(h->comm); h->comm = nullptr; }
+  release_mailboxes(h);
   for (auto& g : h->ig) drop_graph(g);
   if (h->prof_calls > 1 && std::getenv("LOKIB200_PROFILE"))
     std::fprintf(stderr, "lokib200 engine %p: %lld blocking intervals; per interval: submit %.1f us, stream wait %.1f us, outside the call %.1f us\n", static_cast<void*>(h),
@@ -763,6 +774,18 @@ static int flush_pending_hist(lokib200_engine* h) {
   return enqueue_histograms(h, h->hist_pending_phase, nullptr);
 }
 
+// the peer-memory exchange of one engine's result vector (all ranks of the communicator must enqueue theirs)
+static int enqueue_exchange(lokib200_engine* e, double* v, lokib200_engine::IntervalGraph* tap) {
+  lokib200_engine* h = e;
+  CK(cudaSetDevice(e->cfg.device));
+  ++e->exchange_epoch;
+  // (~60 s of spinning: ranks may reach their first exchange seconds apart; a rank that never comes ends as an error, not as a hung GPU)
+  k_exchange<<<1, EXCHANGE_THREADS, 0, e->stream>>>(v, e->part_len, e->mail_stride, e->mail, e->comm_rank, e->comm_size, e->exchange_epoch, 120000000000ll);
+  if (tap) tap->exchange = last_captured_node(e->stream); else ++e->launches;
+  CK(cudaGetLastError());
+  return 0;
+}
+
 // everything one synchronisation interval launches, in stream order; `tap` (capture only) receives the nodes with per-interval arguments
 static int enqueue_interval(lokib200_engine* h, const Model& m, const AdvArgs& a, bool sample, double* d_result, lokib200_engine::IntervalGraph* tap) {
   int rc = 0;
@@ -847,6 +870,7 @@ static int enqueue_result_copy(lokib200_engine* h) {
 static int wait_result(lokib200_engine* h, double* result) {
   CK(cudaStreamSynchronize(h->stream));
   if (result) std::memcpy(result, h->h_result, h->part_len * sizeof(double));
+  if (h->h_result[R_OVERFLOW] == 2.0) return fail(h, LOKIB200_ERR_CUDA, "the exchange of the result vectors timed out: a rank of the communicator did not arrive");
   if (h->h_result[R_OVERFLOW] != 0) return fail(h, LOKIB200_ERR_OVERFLOW, "birth/death list overflow inside one synchronisation interval (on this or another rank)");
   return 0;
 }
@@ -865,7 +889,7 @@ int lokib200_read_result(lokib200_engine* h, double* result) {
 // launch and one stream wait.  Same kernels, same arguments, same order: results are those of the plain launches, which
 // lokib200_advance_to_sync_device keeps using.  LOKIB200_GRAPH=0 selects the plain launches here too, 1 restricts the graph to the thread form.
 static bool graph_eligible(lokib200_engine* h) {
-  if (h->graph_off || h->comm) return false;
+  if (h->graph_off || (h->comm && (!h->p2p || h->comm_local_group))) return false;   // (an NCCL all-reduce is not captured; local groups advance asynchronously)
   static const int mode = [] { const char* e = std::getenv("LOKIB200_GRAPH"); return e ? std::atoi(e) : 2; }();   // 0 = never, 1 = one-electron-per-thread form only, 2 = both forms (default)
   return mode >= 2 || (mode == 1 && !h->use_tile);
 }
@@ -881,19 +905,22 @@ static int advance_graph(lokib200_engine* h, double nu_trial, double t_sync, boo
   const int hist_phase = h->hist_pending_phase;
   h->hist_pending = false;
   lokib200_engine::IntervalGraph& g = h->ig[(sample ? 1 : 0) + (with_hist ? 2 : 0)];
+  const unsigned long long epoch0 = h->exchange_epoch;
   if (!g.exec) {
     bool ok = cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
     if (ok) {
       ok = (!with_hist || enqueue_histograms(h, hist_phase, &g) == 0) && enqueue_interval(h, m, a, sample, nullptr, &g) == 0 &&
+           (!h->comm || enqueue_exchange(h, h->d_result, &g) == 0) &&
            cudaMemcpyAsync(h->h_result, h->d_result, h->part_len * sizeof(double), cudaMemcpyDeviceToHost, h->stream) == cudaSuccess;
       ok = (cudaStreamEndCapture(h->stream, &g.graph) == cudaSuccess) && ok && g.graph && g.k1 && (!h->has_pc || (g.pc_copy && g.pc_lottery)) && (!with_hist || g.hist) &&
-           (!(h->has_pc && h->use_tile) || g.births);
+           (!(h->has_pc && h->use_tile) || g.births) && (!h->comm || g.exchange);
     }
     if (ok) ok = cudaGraphInstantiate(&g.exec, g.graph, 0) == cudaSuccess;
     if (ok) ok = cudaGraphKernelNodeGetParams(g.k1, &g.k1_p) == cudaSuccess;
     if (ok && h->has_pc) ok = cudaGraphKernelNodeGetParams(g.pc_copy, &g.copy_p) == cudaSuccess && cudaGraphKernelNodeGetParams(g.pc_lottery, &g.lot_p) == cudaSuccess;
     if (ok && with_hist) ok = cudaGraphKernelNodeGetParams(g.hist, &g.hist_p) == cudaSuccess;
     if (ok && g.births) ok = cudaGraphKernelNodeGetParams(g.births, &g.births_p) == cudaSuccess;
+    if (ok && g.exchange) { ok = cudaGraphKernelNodeGetParams(g.exchange, &g.exchange_p) == cudaSuccess; ++g.kernels; }
     if (ok && with_hist) ++g.kernels;
     if (!ok) {   // no graph on this engine: the plain launches of the same interval
       cudaGetLastError();
@@ -902,6 +929,7 @@ static int advance_graph(lokib200_engine* h, double nu_trial, double t_sync, boo
       if (with_hist && (rc = enqueue_histograms(h, hist_phase, nullptr))) return rc;
       if ((rc = enqueue_interval(h, m, a, sample, nullptr, nullptr))) return rc;
       h->time = t_sync;
+      if (h->comm) { h->exchange_epoch = epoch0; if ((rc = enqueue_exchange(h, h->d_result, nullptr))) return rc; }   // (the failed capture may have counted this exchange)
       if ((rc = enqueue_result_copy(h))) return rc;
       return wait_result(h, result);
     }
@@ -934,6 +962,15 @@ static int advance_graph(lokib200_engine* h, double nu_trial, double t_sync, boo
       CK(cudaGraphExecKernelNodeSetParams(g.exec, g.pc_copy, &p));
       p = g.lot_p; p.kernelParams = pc_args; p.extra = nullptr;
       CK(cudaGraphExecKernelNodeSetParams(g.exec, g.pc_lottery, &p));
+    }
+    if (g.exchange) {   // the epoch every rank stamps on its flags
+      ++h->exchange_epoch;
+      double* v = h->d_result;
+      int len = h->part_len, stride = h->mail_stride, me = h->comm_rank, nr = h->comm_size;
+      long long timeout = 120000000000ll;
+      void* x_args[8] = {&v, &len, &stride, &h->mail, &me, &nr, &h->exchange_epoch, &timeout};
+      p = g.exchange_p; p.kernelParams = x_args; p.extra = nullptr;
+      CK(cudaGraphExecKernelNodeSetParams(g.exec, g.exchange, &p));
     }
     if (with_hist) {   // phase row (AC fields) and, after a regrid, the grid itself
       HistGrid hg = histogram_args(h, hist_phase);
@@ -992,6 +1029,82 @@ int lokib200_comm_unique_id(void* id128) {
   return 0;
 }
 
+// ---- mailboxes of the peer-memory exchange ----
+static size_t mailbox_bytes(int n_ranks, int stride) { return (2ull * n_ranks * stride) * sizeof(double) + 2ull * n_ranks * sizeof(unsigned long long); }
+static bool p2p_wanted() { const char* e = std::getenv("LOKIB200_P2P"); return !(e && e[0] == '0'); }   // (read when a communicator is created)
+
+static void release_mailboxes(lokib200_engine* h) {
+  for (int r = 0; r < EXCHANGE_MAX_RANKS; ++r) { if (h->mail_ipc[r] && h->mail.box[r]) cudaIpcCloseMemHandle(h->mail.box[r]); h->mail_ipc[r] = false; h->mail.box[r] = nullptr; }
+  if (h->d_mail) { cudaFree(h->d_mail); h->d_mail = nullptr; }
+  h->p2p = false; h->exchange_epoch = 0;
+}
+static bool alloc_mailbox(lokib200_engine* h) {
+  h->mail_stride = (h->part_len + 15) / 16 * 16;
+  const size_t bytes = mailbox_bytes(h->comm_size, h->mail_stride);
+  if (cudaSetDevice(h->cfg.device) != cudaSuccess || cudaMalloc(&h->d_mail, bytes) != cudaSuccess) { cudaGetLastError(); h->d_mail = nullptr; return false; }
+  return cudaMemset(h->d_mail, 0, bytes) == cudaSuccess && cudaDeviceSynchronize() == cudaSuccess;
+}
+// engines of ONE process: peer access between their devices, mailboxes addressed directly
+static void setup_p2p_local(lokib200_engine* const* engines, int n) {
+  if (!p2p_wanted() || n < 2 || n > EXCHANGE_MAX_RANKS) return;
+  bool ok = true;
+  for (int i = 0; i < n && ok; ++i) {
+    for (int j = 0; j < n && ok; ++j) {
+      if (i == j) continue;
+      int can = 0;
+      ok = cudaDeviceCanAccessPeer(&can, engines[i]->cfg.device, engines[j]->cfg.device) == cudaSuccess && can;
+      if (ok) {
+        cudaSetDevice(engines[i]->cfg.device);
+        const cudaError_t e = cudaDeviceEnablePeerAccess(engines[j]->cfg.device, 0);
+        if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError(); else ok = e == cudaSuccess;
+      }
+    }
+  }
+  for (int i = 0; i < n && ok; ++i) ok = alloc_mailbox(engines[i]);
+  if (!ok) { cudaGetLastError(); for (int i = 0; i < n; ++i) release_mailboxes(engines[i]); return; }
+  for (int i = 0; i < n; ++i) { for (int r = 0; r < n; ++r) engines[i]->mail.box[r] = engines[r]->d_mail; engines[i]->p2p = true; }
+}
+// one engine per process: the 64-byte IPC handles of the mailboxes travel through the communicator once (ncclAllGather)
+static void setup_p2p_ipc(lokib200_engine* h, NcclApi* nc) {
+  if (!p2p_wanted() || h->comm_size < 2 || h->comm_size > EXCHANGE_MAX_RANKS || !nc->AllGather) return;
+  const int n = h->comm_size;
+  // every rank must take the same decision, so failures are exchanged too: byte 64 of a rank's record says "my mailbox exists"
+  constexpr int REC = 128;
+  unsigned char mine[REC] = {};
+  if (alloc_mailbox(h)) {
+    cudaIpcMemHandle_t hd;
+    if (cudaIpcGetMemHandle(&hd, h->d_mail) == cudaSuccess) { static_assert(sizeof(hd) == 64, "IPC handle size"); std::memcpy(mine, &hd, 64); mine[64] = 1; }
+    else cudaGetLastError();
+  }
+  unsigned char* d_rec = nullptr;
+  std::vector<unsigned char> all(static_cast<size_t>(REC) * n);
+  bool ok = cudaMalloc(&d_rec, all.size() + REC) == cudaSuccess;
+  if (ok) ok = cudaMemcpy(d_rec + all.size(), mine, REC, cudaMemcpyHostToDevice) == cudaSuccess;
+  if (ok) ok = nc->AllGather(d_rec + all.size(), d_rec, REC, ncclChar, h->comm, h->stream) == ncclSuccess;
+  if (ok) ok = cudaStreamSynchronize(h->stream) == cudaSuccess && cudaMemcpy(all.data(), d_rec, all.size(), cudaMemcpyDeviceToHost) == cudaSuccess;
+  if (d_rec) cudaFree(d_rec);
+  for (int r = 0; r < n && ok; ++r) ok = all[static_cast<size_t>(r) * REC + 64] == 1;
+  int opened = 1;
+  for (int r = 0; r < n && ok; ++r) {
+    if (r == h->comm_rank) { h->mail.box[r] = h->d_mail; continue; }
+    cudaIpcMemHandle_t hd;
+    std::memcpy(&hd, all.data() + static_cast<size_t>(r) * REC, 64);
+    void* q = nullptr;
+    if (cudaIpcOpenMemHandle(&q, hd, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess) { h->mail.box[r] = static_cast<double*>(q); h->mail_ipc[r] = true; ++opened; }
+    else { cudaGetLastError(); break; }
+  }
+  // second round: a rank that could not map a peer must keep everybody on the NCCL path
+  unsigned char* d_flag = nullptr;
+  std::vector<unsigned char> flags(n);
+  const unsigned char my_ok = (ok && opened == n) ? 1 : 0;
+  bool ok2 = cudaMalloc(&d_flag, n + 1) == cudaSuccess && cudaMemcpy(d_flag + n, &my_ok, 1, cudaMemcpyHostToDevice) == cudaSuccess &&
+             nc->AllGather(d_flag + n, d_flag, 1, ncclChar, h->comm, h->stream) == ncclSuccess && cudaStreamSynchronize(h->stream) == cudaSuccess &&
+             cudaMemcpy(flags.data(), d_flag, n, cudaMemcpyDeviceToHost) == cudaSuccess;
+  if (d_flag) cudaFree(d_flag);
+  for (int r = 0; r < n && ok2; ++r) ok2 = flags[r] == 1;
+  if (ok2) h->p2p = true; else { cudaGetLastError(); release_mailboxes(h); }
+}
+
 int lokib200_comm_init_rank(lokib200_engine* h, const void* id128, int32_t rank, int32_t n_ranks) {
   if (!h || !id128 || n_ranks < 1 || rank < 0 || rank >= n_ranks) return fail(h, LOKIB200_ERR_INVALID, "bad communicator arguments");
   NcclApi* nc = nccl_api();
@@ -1002,6 +1115,7 @@ int lokib200_comm_init_rank(lokib200_engine* h, const void* id128, int32_t rank,
   std::memcpy(&id, id128, sizeof(id));
   NK(nc->CommInitRank(&h->comm, n_ranks, id, rank));
   h->comm_size = n_ranks; h->comm_rank = rank; h->comm_local_group = false;
+  setup_p2p_ipc(h, nc);   // (collective; without peer access every rank stays on the NCCL all-reduce)
   return 0;
 }
 
@@ -1019,6 +1133,7 @@ int lokib200_comm_init_all(lokib200_engine* const* engines, int32_t n) {
   std::vector<ncclComm_t> comms(n);
   NK(nc->CommInitAll(comms.data(), n, devs.data()));
   for (int i = 0; i < n; ++i) { engines[i]->comm = comms[i]; engines[i]->comm_size = n; engines[i]->comm_rank = i; engines[i]->comm_local_group = n > 1; }
+  setup_p2p_local(engines, n);
   return 0;
 }
 
@@ -1029,11 +1144,13 @@ int lokib200_comm_destroy(lokib200_engine* h) {
   CK(cudaSetDevice(h->cfg.device));
   CK(cudaStreamSynchronize(h->stream));
   NK(nc->CommDestroy(h->comm));
+  release_mailboxes(h);
   h->comm = nullptr; h->comm_size = 1; h->comm_rank = 0; h->comm_local_group = false;
   return 0;
 }
 
 int32_t lokib200_comm_size(const lokib200_engine* h) { return h ? h->comm_size : 0; }
+const char* lokib200_comm_transport(const lokib200_engine* h) { return (!h || !h->comm) ? "none" : (h->p2p ? "peer-memory" : "nccl"); }
 
 int lokib200_comm_allreduce_results(lokib200_engine* const* engines, int32_t n, double* const* d_results) {
   if (!engines || n < 1 || !engines[0]) return LOKIB200_ERR_INVALID;
@@ -1041,6 +1158,15 @@ int lokib200_comm_allreduce_results(lokib200_engine* const* engines, int32_t n, 
   NcclApi* nc = nccl_api();
   if (!nc->ok) return fail(h, LOKIB200_ERR_CUDA, nc->why);
   for (int i = 0; i < n; ++i) if (!engines[i] || !engines[i]->comm || engines[i]->part_len != h->part_len) return fail(h, LOKIB200_ERR_INVALID, "engine without a communicator / different process sets");
+  bool p2p = true;
+  for (int i = 0; i < n; ++i) p2p = p2p && engines[i]->p2p;
+  if (p2p) {   // one k_exchange launch per engine: vectors pushed into the peers' mailboxes over NVLink, summed in rank order on every rank
+    for (int i = 0; i < n; ++i) {
+      const int rc = enqueue_exchange(engines[i], (d_results && d_results[i]) ? d_results[i] : engines[i]->d_result, nullptr);
+      if (rc) { if (engines[i] != h) h->err = engines[i]->err; return rc; }
+    }
+    return 0;
+  }
   // one NCCL group: [0, SUM_COUNT) by sum, [SUM_COUNT, HEADER) by max, [HEADER, L) by sum -- in place, on each engine's stream
   NK(nc->GroupStart());
   for (int i = 0; i < n; ++i) {

@@ -46,8 +46,11 @@ def test_single_rank_communicator_is_identity():
         assert np.array_equal(a, b)
 
 
+@pytest.mark.parametrize("p2p", ["1", "0"])
 @pytest.mark.parametrize("name", ["reid_acb", "air"])
-def test_two_engines_share_a_communicator(name):
+def test_two_engines_share_a_communicator(name, p2p, monkeypatch):
+    """both transports of the exchange: the peer-memory kernel (k_exchange) and the grouped NCCL all-reduce (LOKIB200_P2P=0)"""
+    monkeypatch.setenv("LOKIB200_P2P", p2p)
     import loki_mc_b200 as lk
     R = lk.R
     if _n_devices() < 2:
@@ -67,6 +70,9 @@ def test_two_engines_share_a_communicator(name):
     engs = [T._engine(g, h, seed=77, device=d, first_electron_id=d * h) for d in range(2)]
     lk.comm_init_all(engs)
     assert all(e.comm_size() == 2 for e in engs)
+    if p2p == "0":
+        assert all(e.comm_transport() == "nccl" for e in engs)
+    print("transport:", engs[0].comm_transport())
     for d, e in enumerate(engs):
         e.build_tables(maxE); e.set_ensemble(s0[:, d * h:(d + 1) * h], 0.0)
 
@@ -117,3 +123,42 @@ def test_two_engine_job_equals_one_engine_job():
     assert np.allclose(a["flux_drift_velocity"], b["flux_drift_velocity"], rtol=1e-8, atol=1e-9 * abs(a["flux_drift_velocity"][2]))
     assert np.array_equal(out[0][1]["eeh"], out[1][1]["eeh"])      # histograms: combined once per job, counts are integers
     assert np.array_equal(out[0][1]["eah"], out[1][1]["eah"])
+
+
+@pytest.mark.timeout(600)
+@pytest.mark.parametrize("p2p", ["1", "0"])
+def test_two_processes_exchange_over_ipc(p2p, tmp_path):
+    """one engine per process (torchrun): mailboxes mapped through CUDA IPC, the exchange kernel a node of the graph-launched blocking interval;
+    both ranks must return the SAME bits, equal to the one-engine ensemble (counters exact, sums up to the order of addition)"""
+    import os
+    import subprocess
+    import sys
+    import loki_mc_b200 as lk
+    R = lk.R
+    if _n_devices() < 2:
+        pytest.skip("needs two GPUs")
+    name, n = "reid_acb", 200_000
+    here = os.path.dirname(os.path.abspath(__file__))
+    env = dict(os.environ, LOKIB200_P2P=p2p)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1", "--master-port", "29631",
+                        os.path.join(here, "_two_rank_worker.py"), str(tmp_path), name, str(n)], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=500)
+    assert r.returncode == 0, r.stdout[-3000:]
+    a, b = np.load(tmp_path / "rank0.npy"), np.load(tmp_path / "rank1.npy")
+    transport = open(tmp_path / "rank0.txt").read()
+    assert transport == open(tmp_path / "rank1.txt").read() and transport in (("nccl",) if p2p == "0" else ("peer-memory", "nccl"))
+    print("transport:", transport)
+    assert np.array_equal(a, b)
+    g = gio.load(name)
+    s0 = T._start_state(g, n, np.random.default_rng(5), 1e-2, 5.0)
+    one = T._engine(g, n, seed=77)
+    one.build_tables(12.0); nu = one.table_info()["nu_max_last"]; one.set_ensemble(s0, 0.0)
+    want = [one.advance(nu, it / nu, sample=(it != 2)) for it in range(1, 6)]
+    one.close()
+    P = (a.shape[1] - R.HEADER) // 3
+    for it, (w, got) in enumerate(zip(want, a)):
+        for j in (R.N_REAL, R.N_NULL, R.N_BORN, R.N_ATTACHED, R.N_SAMPLED):
+            assert w[j] == got[j], (it, j)
+        assert np.array_equal(w[R.HEADER:R.HEADER + P], got[R.HEADER:R.HEADER + P])
+        if w[R.N_SAMPLED] > 0:
+            assert abs(w[R.SUM_EPS] - got[R.SUM_EPS]) <= 1e-11 * w[R.SUM_EPS]
+        assert got[R.OVERFLOW] == 0
