@@ -481,18 +481,22 @@ __device__ __forceinline__ void copy_birth_to_slot(const State& s, const Lists& 
   s.tcf[slot] = src[6 * c]; s.nue[slot] = src[7 * c];
 }
 
-__global__ void k_pc_fill(const State s, const Lists L) {
+// The five phases as device functions over a thread range [first, first + step, ...): the general path runs each as its own grid (a grid-wide
+// dependency separates them), k_pc_small runs all of them in ONE CTA with barriers in between (small ensembles: the lists hold a few entries and
+// five launches cost more than the work).
+__device__ __forceinline__ void pc_fill(const State& s, const Lists& L, unsigned int first, unsigned int step) {
   const unsigned int nB = min(L.counters[C_BIRTHS], L.birth_cap), nD = min(L.counters[C_DEAD], L.dead_cap), nF = min(nB, nD);
-  for (unsigned int j = blockIdx.x * blockDim.x + threadIdx.x; j < nF; j += gridDim.x * blockDim.x) {
+  for (unsigned int j = first; j < nF; j += step) {
     const unsigned int slot = L.dead[j];
     copy_birth_to_slot(s, L, slot, nB - 1 - j);
     L.dead_flag[slot] = 0;
   }
 }
 
-__global__ void k_pc_copy(const State s, const Lists L, long long n, unsigned long long first_id, unsigned long long seed, unsigned int interval) {
+__device__ __forceinline__ void pc_copy(const State& s, const Lists& L, long long n, unsigned long long first_id, unsigned long long seed, unsigned int interval,
+                                        unsigned int first, unsigned int step) {
   const unsigned int nB = min(L.counters[C_BIRTHS], L.birth_cap), nD = min(L.counters[C_DEAD], L.dead_cap);
-  for (unsigned int j = nB + blockIdx.x * blockDim.x + threadIdx.x; j < nD; j += gridDim.x * blockDim.x) {
+  for (unsigned int j = nB + first; j < nD; j += step) {
     const unsigned int slot = L.dead[j];
     PhiloxRng rng; rng.init(seed, first_id + slot, interval, 0); rng.c2 = interval; rng.c1 |= POPCTRL_INTERVAL_BIT;
     long long donor = 0;
@@ -507,12 +511,13 @@ __global__ void k_pc_copy(const State s, const Lists L, long long n, unsigned lo
   }
 }
 
-__global__ void k_pc_lottery(const State s, const Lists L, long long n, unsigned long long first_id, unsigned long long seed, unsigned int interval) {
+__device__ __forceinline__ void pc_lottery(const State& s, const Lists& L, long long n, unsigned long long first_id, unsigned long long seed, unsigned int interval,
+                                           unsigned int first, unsigned int step) {
   const unsigned int nB = min(L.counters[C_BIRTHS], L.birth_cap), nD = min(L.counters[C_DEAD], L.dead_cap);
   if (nB <= nD) return;
   const unsigned int K = nB - nD;
   const double pool = static_cast<double>(n) + static_cast<double>(K);
-  for (unsigned int b = blockIdx.x * blockDim.x + threadIdx.x; b < K; b += gridDim.x * blockDim.x) {
+  for (unsigned int b = first; b < K; b += step) {
     PhiloxRng rng; rng.init(seed, first_id + static_cast<unsigned long long>(n) + b, interval, 0); rng.c1 |= POPCTRL_INTERVAL_BIT;
     long long j = 0;
     for (int it = 0; it < 1 << 20; ++it) {                                // sampling without replacement by rejection
@@ -531,35 +536,64 @@ __global__ void k_pc_lottery(const State s, const Lists L, long long n, unsigned
   }
 }
 
-__global__ void k_pc_place(const State s, const Lists L, long long n) {
+__device__ __forceinline__ void pc_place(const State& s, const Lists& L, long long n, unsigned int first, unsigned int step) {
   const unsigned int nB = min(L.counters[C_BIRTHS], L.birth_cap), nD = min(L.counters[C_DEAD], L.dead_cap);
   if (nB <= nD) return;
   const unsigned int K = nB - nD;
-  for (unsigned int b = blockIdx.x * blockDim.x + threadIdx.x; b < K; b += gridDim.x * blockDim.x) {
+  for (unsigned int b = first; b < K; b += step) {
     if (L.claim[n + b] == 0u) copy_birth_to_slot(s, L, L.freed[atomicAdd(&L.counters[C_PLACED], 1u)], b);
   }
 }
 
-// sums the growth terms in a fixed order into pc_result[0], clears claims / flags / counters for the next interval
-__global__ void k_pc_reset(const Lists L, long long n, double* pc_result) {
+// sums the growth terms in a fixed order into pc_result[0], clears claims / flags / counters for the next interval (one CTA)
+__device__ __forceinline__ void pc_reset(const Lists& L, long long n, double* pc_result, double* red /* [blockDim.x] shared */) {
   const unsigned int nB = min(L.counters[C_BIRTHS], L.birth_cap), nD = min(L.counters[C_DEAD], L.dead_cap);
   const unsigned int K = (nB > nD) ? nB - nD : 0u, nFreed = L.counters[C_FREED], nTerms = L.counters[C_TERMS];
   for (unsigned int b = threadIdx.x; b < K; b += blockDim.x) L.claim[n + b] = 0u;
   for (unsigned int f = threadIdx.x; f < nFreed; f += blockDim.x) L.claim[L.freed[f]] = 0u;
   for (unsigned int j = threadIdx.x; j < nD; j += blockDim.x) L.dead_flag[L.dead[j]] = 0;
-  __shared__ double red[256];
   double acc = 0;
   for (unsigned int t = threadIdx.x; t < nTerms; t += blockDim.x) acc += L.growth_terms[t];
   red[threadIdx.x] = acc;
   __syncthreads();
   if (threadIdx.x == 0) {
     double tot = 0;
-    for (int t = 0; t < 256; ++t) tot += red[t];
+    for (unsigned int t = 0; t < blockDim.x; ++t) tot += red[t];
     pc_result[0] = tot;
     pc_result[1] = static_cast<double>(L.counters[C_OVERFLOW]);
   }
   __syncthreads();
   if (threadIdx.x < C_COUNT) L.counters[threadIdx.x] = 0u;
+}
+
+__global__ void k_pc_fill(const State s, const Lists L) { pc_fill(s, L, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x); }
+__global__ void k_pc_copy(const State s, const Lists L, long long n, unsigned long long first_id, unsigned long long seed, unsigned int interval) {
+  pc_copy(s, L, n, first_id, seed, interval, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x);
+}
+__global__ void k_pc_lottery(const State s, const Lists L, long long n, unsigned long long first_id, unsigned long long seed, unsigned int interval) {
+  pc_lottery(s, L, n, first_id, seed, interval, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x);
+}
+__global__ void k_pc_place(const State s, const Lists L, long long n) { pc_place(s, L, n, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x); }
+__global__ void k_pc_reset(const Lists L, long long n, double* pc_result) {
+  __shared__ double red[256];
+  pc_reset(L, n, pc_result, red);
+}
+
+// all five phases in one CTA: each phase reads what the previous one wrote (ensemble slots, claims, counters), so a CTA barrier - which also
+// orders the CTA's global-memory accesses - stands where the general path has a kernel boundary
+constexpr int PC_SMALL_THREADS = 256;
+__global__ void __launch_bounds__(PC_SMALL_THREADS) k_pc_small(const State s, const Lists L, long long n, unsigned long long first_id, unsigned long long seed,
+                                                               unsigned int interval, double* pc_result) {
+  __shared__ double red[PC_SMALL_THREADS];
+  pc_fill(s, L, threadIdx.x, PC_SMALL_THREADS);
+  __syncthreads();
+  pc_copy(s, L, n, first_id, seed, interval, threadIdx.x, PC_SMALL_THREADS);
+  __syncthreads();
+  pc_lottery(s, L, n, first_id, seed, interval, threadIdx.x, PC_SMALL_THREADS);
+  __syncthreads();
+  pc_place(s, L, n, threadIdx.x, PC_SMALL_THREADS);
+  __syncthreads();
+  pc_reset(L, n, pc_result, red);
 }
 
 // ------------------------------------------------------------------ finalize ------------------------------------------------------------------

@@ -112,8 +112,8 @@ struct lokib200_engine {
   struct IntervalGraph {
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t exec = nullptr;
-    cudaGraphNode_t k1 = nullptr, births = nullptr, pc_copy = nullptr, pc_lottery = nullptr, hist = nullptr, exchange = nullptr;   // the nodes whose arguments change from interval to interval
-    cudaKernelNodeParams k1_p{}, births_p{}, copy_p{}, lot_p{}, hist_p{}, exchange_p{};
+    cudaGraphNode_t k1 = nullptr, births = nullptr, pc_copy = nullptr, pc_lottery = nullptr, pc_small = nullptr, hist = nullptr, exchange = nullptr;   // the nodes whose arguments change from interval to interval
+    cudaKernelNodeParams k1_p{}, births_p{}, copy_p{}, lot_p{}, small_p{}, hist_p{}, exchange_p{};
     int kernels = 0;
   } ig[4];   // index = sample flag + 2 * (the deferred histogram pass of the previous sample comes first)
   bool graph_off = false;
@@ -774,6 +774,13 @@ static int flush_pending_hist(lokib200_engine* h) {
   return enqueue_histograms(h, h->hist_pending_phase, nullptr);
 }
 
+// population control of a small ensemble runs as ONE single-CTA kernel: its lists hold at most a few thousand entries and five dependent launches
+// cost more than the work (LOKIB200_PC_SMALL=0 keeps the five grids)
+static bool pc_in_one_cta(const lokib200_engine* h) {
+  static const bool on = [] { const char* e = std::getenv("LOKIB200_PC_SMALL"); return !(e && e[0] == '0'); }();
+  return on && h->cfg.n_electrons <= 262144;
+}
+
 // the peer-memory exchange of one engine's result vector (all ranks of the communicator must enqueue theirs)
 static int enqueue_exchange(lokib200_engine* e, double* v, lokib200_engine::IntervalGraph* tap) {
   lokib200_engine* h = e;
@@ -814,7 +821,11 @@ static int enqueue_interval(lokib200_engine* h, const Model& m, const AdvArgs& a
     launch_births(h, m, a); ++kernels; births = h->d_birth_part; CK(cudaGetLastError());
     if (tap) tap->births = last_captured_node(h->stream);
   }
-  if (h->has_pc) {
+  if (h->has_pc && pc_in_one_cta(h)) {   // small ensemble: the five phases in one CTA (lk_kernels.cuh k_pc_small)
+    k_pc_small<<<1, PC_SMALL_THREADS, 0, h->stream>>>(h->st, h->lists, a.n, a.first_id, a.seed, a.interval, h->d_pc_result);
+    if (tap) tap->pc_small = last_captured_node(h->stream);
+    ++kernels;
+  } else if (h->has_pc) {
     const int pcb = std::max(1, std::min(h->sm_count * 2, static_cast<int>((h->lists.birth_cap + 255) / 256)));
     k_pc_fill<<<pcb, 256, 0, h->stream>>>(h->st, h->lists);
     k_pc_copy<<<pcb, 256, 0, h->stream>>>(h->st, h->lists, a.n, a.first_id, a.seed, a.interval);
@@ -912,12 +923,13 @@ static int advance_graph(lokib200_engine* h, double nu_trial, double t_sync, boo
       ok = (!with_hist || enqueue_histograms(h, hist_phase, &g) == 0) && enqueue_interval(h, m, a, sample, nullptr, &g) == 0 &&
            (!h->comm || enqueue_exchange(h, h->d_result, &g) == 0) &&
            cudaMemcpyAsync(h->h_result, h->d_result, h->part_len * sizeof(double), cudaMemcpyDeviceToHost, h->stream) == cudaSuccess;
-      ok = (cudaStreamEndCapture(h->stream, &g.graph) == cudaSuccess) && ok && g.graph && g.k1 && (!h->has_pc || (g.pc_copy && g.pc_lottery)) && (!with_hist || g.hist) &&
+      ok = (cudaStreamEndCapture(h->stream, &g.graph) == cudaSuccess) && ok && g.graph && g.k1 && (!h->has_pc || g.pc_small || (g.pc_copy && g.pc_lottery)) && (!with_hist || g.hist) &&
            (!(h->has_pc && h->use_tile) || g.births) && (!h->comm || g.exchange);
     }
     if (ok) ok = cudaGraphInstantiate(&g.exec, g.graph, 0) == cudaSuccess;
     if (ok) ok = cudaGraphKernelNodeGetParams(g.k1, &g.k1_p) == cudaSuccess;
-    if (ok && h->has_pc) ok = cudaGraphKernelNodeGetParams(g.pc_copy, &g.copy_p) == cudaSuccess && cudaGraphKernelNodeGetParams(g.pc_lottery, &g.lot_p) == cudaSuccess;
+    if (ok && g.pc_small) ok = cudaGraphKernelNodeGetParams(g.pc_small, &g.small_p) == cudaSuccess;
+    if (ok && g.pc_copy) ok = cudaGraphKernelNodeGetParams(g.pc_copy, &g.copy_p) == cudaSuccess && cudaGraphKernelNodeGetParams(g.pc_lottery, &g.lot_p) == cudaSuccess;
     if (ok && with_hist) ok = cudaGraphKernelNodeGetParams(g.hist, &g.hist_p) == cudaSuccess;
     if (ok && g.births) ok = cudaGraphKernelNodeGetParams(g.births, &g.births_p) == cudaSuccess;
     if (ok && g.exchange) { ok = cudaGraphKernelNodeGetParams(g.exchange, &g.exchange_p) == cudaSuccess; ++g.kernels; }
@@ -956,7 +968,12 @@ static int advance_graph(lokib200_engine* h, double nu_trial, double t_sync, boo
       p.kernelParams = k1_args;
       CK(cudaGraphExecKernelNodeSetParams(g.exec, g.k1, &p));
     }
-    if (h->has_pc) {
+    if (g.pc_small) {
+      double* pcr = h->d_pc_result;
+      void* pc_args[7] = {&h->st, &h->lists, &a.n, &a.first_id, &a.seed, &a.interval, &pcr};
+      p = g.small_p; p.kernelParams = pc_args; p.extra = nullptr;
+      CK(cudaGraphExecKernelNodeSetParams(g.exec, g.pc_small, &p));
+    } else if (h->has_pc) {
       void* pc_args[6] = {&h->st, &h->lists, &a.n, &a.first_id, &a.seed, &a.interval};
       p = g.copy_p; p.kernelParams = pc_args; p.extra = nullptr;
       CK(cudaGraphExecKernelNodeSetParams(g.exec, g.pc_copy, &p));
