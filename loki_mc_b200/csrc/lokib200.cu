@@ -533,9 +533,10 @@ int lokib200_set_processes(lokib200_engine* h, const lokib200_process_soa* p) {
   h->tile_blocks = static_cast<int>(std::min<int64_t>((h->cfg.n_electrons + POOL - 1) / POOL, static_cast<int64_t>(h->sm_count) * 2));
   h->birth_blocks = h->sm_count;
   h->smp_blocks = static_cast<int>(std::min<int64_t>((h->cfg.n_electrons + ADV_THREADS - 1) / ADV_THREADS, static_cast<int64_t>(h->sm_count) * 4));
-  // kernel choice: the tile kernel needs enough tiles to fill the machine; LOKIB200_KERNEL=thread|tile overrides
-  // kernel choice: the streaming-pool kernel needs several pools per CTA to amortise its fill/drain; LOKIB200_KERNEL=thread|stream overrides
-  h->use_tile = h->cfg.n_electrons >= static_cast<int64_t>(4) * POOL * 2 * h->sm_count;
+  // kernel choice, measured (tools/form_crossover.py, profiles/r2_form_crossover.txt): the streaming pool wins from ~1e5 electrons on (K1 95 vs 107 us
+  // at 1e5, 111 vs 205 us at 2.5e5, 221 vs 700 us at 1e6 on the N2 workload), one electron per thread below (60 vs 93 us at 5e4).
+  // LOKIB200_KERNEL=thread|stream overrides
+  h->use_tile = h->cfg.n_electrons >= static_cast<int64_t>(96) * POOL;
   if (const char* env = std::getenv("LOKIB200_KERNEL")) { if (!std::strcmp(env, "thread")) h->use_tile = false; else if (!std::strcmp(env, "stream") || !std::strcmp(env, "tile")) h->use_tile = true; }
   if (stream_smem_bytes(P) > STREAM_SMEM_BUDGET) h->use_tile = false;   // more than half an SM's shared memory: fall back to one electron per thread
   for (auto& g : h->ig) drop_graph(g);   // the captured launches hold the buffers released below

@@ -133,8 +133,9 @@ void solveJob(const lokihost::SetupInput& in, const lokib200_process_soa& soa, i
                  t_job_gone - t_fetched, seconds() - t_job_gone);
 }
 
-// an ensemble this small leaves most of a B200 idle (K1 of 2e5 electrons is ~700 warps on 148 SMs x 64 warp slots)
-constexpr int64_t SIDE_BY_SIDE_MAX_ELECTRONS = 250000;
+// an ensemble this small leaves most of a B200 idle: it runs the one-electron-per-thread form of K1 (the engine switches to the streaming pool,
+// which fills the SMs' shared memory, at 96 x 1024 electrons), a few hundred warps on 148 SMs x 64 warp slots
+constexpr int64_t SIDE_BY_SIDE_MAX_ELECTRONS = 96 * 1024 - 1;
 constexpr int SIDE_BY_SIDE_PER_DEVICE = 8;
 
 }  // namespace
