@@ -476,7 +476,7 @@ def main():
     arm.close()
 
     also = []
-    if not args.no_extras:
+    if not args.no_extras and world == 1:   # (the `also` legs describe one GPU; the N > 1 lines carry the headline workload only)
         # more of what BASELINE.json names, each a short leg of the same measurement (same rules: warm-up >= 3, inputs >> L2, CUDA events)
         extra = [dict(tag="configs[1] with histograms every sample (post-steady-state cadence, BoltzmannMC.C:1551-1571)", model=args.model, n=n, S=1.0, hist=True, steps=20),
                  dict(tag="configs[1] at synchronizationTimeXMaxCollisionFrequency = 10 (Headers/BoltzmannMC.h:72)", model=args.model, n=n, S=10.0, hist=False, steps=10),
