@@ -1156,6 +1156,7 @@ int lokib200_comm_init_rank(lokib200_engine* h, const void* id128, int32_t rank,
   std::memcpy(&id, id128, sizeof(id));
   NK(nc->CommInitRank(&h->comm, n_ranks, id, rank));
   h->comm_size = n_ranks; h->comm_rank = rank; h->comm_local_group = false;
+  for (auto& g : h->ig) drop_graph(g);   // a captured interval knows nothing of the exchange
   setup_p2p_ipc(h, nc);   // (collective; without peer access every rank stays on the NCCL all-reduce)
   return 0;
 }
@@ -1174,6 +1175,7 @@ int lokib200_comm_init_all(lokib200_engine* const* engines, int32_t n) {
   std::vector<ncclComm_t> comms(n);
   NK(nc->CommInitAll(comms.data(), n, devs.data()));
   for (int i = 0; i < n; ++i) { engines[i]->comm = comms[i]; engines[i]->comm_size = n; engines[i]->comm_rank = i; engines[i]->comm_local_group = n > 1; }
+  for (int i = 0; i < n; ++i) for (auto& g : engines[i]->ig) drop_graph(g);
   setup_p2p_local(engines, n);
   return 0;
 }
@@ -1185,6 +1187,7 @@ int lokib200_comm_destroy(lokib200_engine* h) {
   CK(cudaSetDevice(h->cfg.device));
   CK(cudaStreamSynchronize(h->stream));
   NK(nc->CommDestroy(h->comm));
+  for (auto& g : h->ig) drop_graph(g);   // (their exchange node addresses the mailboxes released below)
   release_mailboxes(h);
   h->comm = nullptr; h->comm_size = 1; h->comm_rank = 0; h->comm_local_group = false;
   return 0;
