@@ -193,7 +193,7 @@ class StdoutToStderr:
         os.close(self.saved)
 
 
-def run_time_to_3sigma(which="default", with_reference=True, fast_mode=False):
+def run_time_to_3sigma(which="default", with_reference=True, fast_mode=False, reps=1):
     """BASELINE.json's second metric: wall time from job start until the run's own stop criterion is met with every swarm parameter within
     3 sigma_eff of the reference, through the setup-file entry point (lokib200_run_setup: parse -> solve -> post-process ->
     write the output folder).
@@ -233,9 +233,13 @@ def run_time_to_3sigma(which="default", with_reference=True, fast_mode=False):
         f.write(warm)
     with StdoutToStderr():
         lk.run_setup(inp, os.path.join(tmp, "warm.in"), os.path.join(tmp, "warm"), verbose=False)          # untimed: context creation, module load
-        t0 = time.perf_counter()
-        lk.run_setup(inp, path, os.path.join(tmp, "out"), verbose=False)
-        wall = time.perf_counter() - t0
+        walls = []
+        for rep in range(max(1, reps)):   # the same job (same seeds) several times: the wall clock of a shared box scatters by +-30 %, the results do not
+            shutil.rmtree(os.path.join(tmp, "out"), ignore_errors=True)
+            t0 = time.perf_counter()
+            lk.run_setup(inp, path, os.path.join(tmp, "out"), verbose=False)
+            walls.append(time.perf_counter() - t0)
+        wall = float(np.median(walls))
     worst, checked, events, worst_key = 0.0, 0, 0.0, ""
     for sub in sorted(os.listdir(os.path.join(tmp, "out", folder))):
         d = os.path.join(tmp, "out", folder, sub)
@@ -259,7 +263,7 @@ def run_time_to_3sigma(which="default", with_reference=True, fast_mode=False):
                             schedule="the jobs of the sweep side by side on the one GPU (an engine, stream and host thread each; LOKIB200_CONCURRENT_JOBS=%s), every "
                                      "blocking interval one CUDA graph launch; reports written in job order" % os.environ.get("LOKIB200_CONCURRENT_JOBS", "auto")),
                 within_3sigma=bool(worst <= 3.0), worst_deviation_sigma=worst, worst_parameter=worst_key, parameters_checked=checked, events=events,
-                events_per_s=events / wall)
+                events_per_s=events / wall, runs=[round(w, 4) for w in walls], value_is="median of `runs`")
     if which == "default":
         line["reference_recorded"] = dict(value=float(np.mean(gj["wall"])), unit="s", cores=gj["threads"], kind="reference",
                                           sample="unmodified lokimc on the same setup, %d replicas in the build container (oracle/gen_default_setup_golden.py)" % len(gj["wall"]))
@@ -432,12 +436,13 @@ def main():
     ap.add_argument("--no-extras", action="store_true", help="only the headline workload (skip the `also` legs and time_to_3sigma)")
     ap.add_argument("--time-to-3sigma", action="store_true", help="second metric of BASELINE.json alone: setup file in, swarm parameters out, on one GPU")
     ap.add_argument("--t3s-setup", default="default", choices=["default", "fixture"])
+    ap.add_argument("--t3s-reps", type=int, default=1, help="with --time-to-3sigma: repetitions of the timed run (value = median)")
     ap.add_argument("--t3s-no-reference", action="store_true", help="with --time-to-3sigma: do not run the reference beside it (its recorded time is quoted)")
     ap.add_argument("--fast-mode", action="store_true", help="with --time-to-3sigma: numericsMC.fastMode: true")
     args = ap.parse_args()
     claim_stdout()
     if args.time_to_3sigma:
-        emit(run_time_to_3sigma(args.t3s_setup, with_reference=not args.t3s_no_reference, fast_mode=args.fast_mode))
+        emit(run_time_to_3sigma(args.t3s_setup, with_reference=not args.t3s_no_reference, fast_mode=args.fast_mode, reps=args.t3s_reps))
         return
     if args.warmup < 3:
         args.warmup = 3
@@ -539,12 +544,12 @@ def main():
             try:   # BASELINE.json's second metric on configs[0], Code/Input/default_setup.in verbatim
                 # (its own process, as a user runs lokimc_b200: this one holds torch, the clock sampler and the OpenMP team of the CPU baseline)
                 def t3s(*extra):
-                    out = subprocess.run([sys.executable, os.path.abspath(__file__), "--time-to-3sigma", "--t3s-no-reference", *extra], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL,
+                    out = subprocess.run([sys.executable, os.path.abspath(__file__), "--time-to-3sigma", "--t3s-no-reference", "--t3s-reps", "3", *extra], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL,
                                          text=True, timeout=900).stdout
                     return json.loads([l for l in out.splitlines() if l.startswith("{")][-1])
                 line["time_to_3sigma"] = t3s()
                 fm = t3s("--fast-mode")
-                line["time_to_3sigma"]["fast_mode"] = dict(value=fm["value"], unit="s", within_3sigma=fm["within_3sigma"], worst_deviation_sigma=fm["worst_deviation_sigma"], worst_parameter=fm["worst_parameter"],
+                line["time_to_3sigma"]["fast_mode"] = dict(value=fm["value"], unit="s", runs=fm.get("runs"), within_3sigma=fm["within_3sigma"], worst_deviation_sigma=fm["worst_deviation_sigma"], worst_parameter=fm["worst_parameter"],
                                                            events=fm["events"], note="numericsMC.fastMode: true (per-energy-band trial frequencies; not a reference key)")
             except Exception as ex:
                 line["time_to_3sigma"] = dict(value=None, error=str(ex))
