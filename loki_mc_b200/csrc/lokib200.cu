@@ -805,13 +805,16 @@ static bool pc_in_one_cta(const lokib200_engine* h) {
   return on && h->cfg.n_electrons <= 262144;
 }
 
+// spin limit of the exchange kernel, ~60 s of SM clocks: ranks may reach their first exchange seconds apart; a rank that never comes ends as an
+// error code in the vector, not as a hung GPU
+constexpr long long EXCHANGE_TIMEOUT_CYCLES = 120000000000ll;
+
 // the peer-memory exchange of one engine's result vector (all ranks of the communicator must enqueue theirs)
 static int enqueue_exchange(lokib200_engine* e, double* v, lokib200_engine::IntervalGraph* tap) {
   lokib200_engine* h = e;
   CK(cudaSetDevice(e->cfg.device));
   ++e->exchange_epoch;
-  // (~60 s of spinning: ranks may reach their first exchange seconds apart; a rank that never comes ends as an error, not as a hung GPU)
-  k_exchange<<<1, EXCHANGE_THREADS, 0, e->stream>>>(v, e->part_len, e->mail_stride, e->mail, e->comm_rank, e->comm_size, e->exchange_epoch, 120000000000ll);
+  k_exchange<<<1, EXCHANGE_THREADS, 0, e->stream>>>(v, e->part_len, e->mail_stride, e->mail, e->comm_rank, e->comm_size, e->exchange_epoch, EXCHANGE_TIMEOUT_CYCLES);
   if (tap) tap->exchange = last_captured_node(e->stream); else ++e->launches;
   CK(cudaGetLastError());
   return 0;
@@ -1008,7 +1011,7 @@ static int advance_graph(lokib200_engine* h, double nu_trial, double t_sync, boo
       ++h->exchange_epoch;
       double* v = h->d_result;
       int len = h->part_len, stride = h->mail_stride, me = h->comm_rank, nr = h->comm_size;
-      long long timeout = 120000000000ll;
+      long long timeout = EXCHANGE_TIMEOUT_CYCLES;
       void* x_args[8] = {&v, &len, &stride, &h->mail, &me, &nr, &h->exchange_epoch, &timeout};
       p = g.exchange_p; p.kernelParams = x_args; p.extra = nullptr;
       CK(cudaGraphExecKernelNodeSetParams(g.exec, g.exchange, &p));
