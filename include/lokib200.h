@@ -165,7 +165,9 @@ double lokib200_time(const lokib200_engine* h);
  *     performCollision :907-1113, conservative/ionization/attachmentCollision :1115-1280, nonParallelCollisionTasks :1282-1408,
  *     and, when `sample` != 0, the ensemble sums of calculateMeanDataForSwarmParams :1410-1454) ---
  * Advances every electron from the engine's time to t_sync with trial frequency nu_trial, applies birth/death population
- * control at t_sync, and writes LOKIB200_RESULT_LEN(P) doubles to `result` (host memory; may be NULL). */
+ * control at t_sync, and writes LOKIB200_RESULT_LEN(P) doubles to `result` (host memory; may be NULL).
+ * Blocking.  The whole interval (advance kernel ... copy of the vector into pinned memory, and the peer-memory exchange of a
+ * communicator) is ONE CUDA graph launch, captured on the first call (LOKIB200_GRAPH=0: individual launches; identical results). */
 int lokib200_advance_to_sync(lokib200_engine* h, double nu_trial, double t_sync, int32_t sample, double* result);
 /* same, asynchronous: the result stays in device memory (`d_result`, >= LOKIB200_RESULT_LEN(P) doubles, caller-owned device
  * pointer, e.g. a torch tensor that is then all-reduced over NCCL); no host synchronisation */
@@ -202,7 +204,10 @@ int lokib200_comm_allreduce_histograms(lokib200_engine* const* engines, int32_t 
 /* --- distributions (replaces: getTimeDependDistributions BMC.C:1492-1572, histogramCount / histogram2DCount MathFunctions.C:61-127) ---
  * grids are those of checkSteadyState (BMC.C:1862-1883): energy [0,max_eedf_energy], cos in [-1,1], v_r in [0,v_max], v_z in [-v_max,v_max] */
 int lokib200_set_histogram_grid(lokib200_engine* h, double max_eedf_energy);   /* also zeroes the accumulators */
-int lokib200_sample_histograms(lokib200_engine* h, int32_t phase_index);        /* phase_index < 0: no phase-resolved EEDF */
+/* counts the current ensemble (phase_index < 0: no phase-resolved EEDF).  On an engine that advances by graph launches the pass is queued into
+ * the front of the next interval (the ensemble does not change in between); lokib200_fetch_histograms, a regrid, a new grid or ensemble, or
+ * lokib200_advance_to_sync_device run it first, so a caller never observes the difference. */
+int lokib200_sample_histograms(lokib200_engine* h, int32_t phase_index);
 /* accumulated counts as doubles (eehSum [nE], eahSum [nE][nCos], evhSum [nR][nA], eehSum_periodic [nPhases][nE]); any may be NULL */
 int lokib200_fetch_histograms(lokib200_engine* h, double* eeh, double* eah, double* evh, double* eeh_periodic);
 
