@@ -478,6 +478,7 @@ def main():
                   "peer-memory": "in-engine exchange over peer memory every interval: one kernel per GPU pushes its result vector into every peer's mailbox (NVLink stores) and adds "
                                  "the slots in rank order (k_exchange); a graph node of the blocking call",
                   "nccl": "in-engine grouped ncclAllReduce per interval (LOKIB200_P2P=0, or no peer access between the GPUs)"}[transport]
+    arm.barrier()   # (every rank has left its last exchange before any mailbox goes away)
     arm.close()
 
     also = []
