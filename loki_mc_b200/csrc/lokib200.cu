@@ -623,6 +623,26 @@ int lokib200_build_tables(lokib200_engine* h, double max_energy) {
   h->h_nu_tot.assign(nE, 0.0); h->h_nu_max.assign(nE, 0.0);
   const double Ngas = h->cfg.gas_density;
   double running_max = 0;
+  // The rows are visited with rising energy, so the bracket of every process only moves forward: a cursor per process replaces the bisection of
+  // lin_interp (the table is rebuilt ~5 times per job while the swarm heats up; 1e4 rows x P processes).  Same bracket - the largest j <= n - 2 with
+  // x[j] <= xv - hence the same doubles (checked on all 22 golden process sets, 1.3e7 brackets); a cross section whose energies are not sorted keeps the bisection.
+  std::vector<int64_t> cursor(static_cast<size_t>(P), 0);
+  std::vector<char> sorted(static_cast<size_t>(P), 1);
+  for (int k = 0; k < P; ++k) {
+    const int64_t o = h->xs_off[k], n = h->xs_off[k + 1] - o;
+    for (int64_t j = 1; j < n; ++j) if (h->xs_e[o + j] < h->xs_e[o + j - 1]) { sorted[k] = 0; break; }
+    if (n < 2) sorted[k] = 0;
+  }
+  auto interpolate = [&](int table, int k, double xv) {   // cross section `table` at xv; the cursor belongs to process k (a superelastic reads its parent's table)
+    const int64_t o = h->xs_off[table], n = h->xs_off[table + 1] - o;
+    const double* x = h->xs_e.data() + o;
+    const double* y = h->xs_v.data() + o;
+    if (!sorted[table]) return lin_interp(x, y, n, xv);
+    int64_t& c = cursor[k];
+    while (c + 1 <= n - 2 && x[c + 1] <= xv) ++c;
+    const double dx = x[c + 1] - x[c];
+    return y[c] + (xv - x[c]) / dx * (y[c + 1] - y[c]);
+  };
   for (int i = 0; i < nE; ++i) {
     const double energy = i * h->dE;
     double acc = 0;
@@ -630,13 +650,10 @@ int lokib200_build_tables(lokib200_engine* h, double max_energy) {
     for (int k = 0; k < P; ++k) {
       double value = 0;
       if (h->superel[k]) {                                                // Klein-Rosseland, BMC.C:584-595
-        if (energy > h->emin[k] && energy <= h->emax[k]) {
-          const int64_t o = h->xs_off[k - 1], n = h->xs_off[k] - o;
-          value = h->swf[k] * (1.0 + h->emin[k - 1] / energy) * lin_interp(h->xs_e.data() + o, h->xs_v.data() + o, n, energy + h->emin[k - 1]) * h->reldens[k];
-        }
+        if (energy > h->emin[k] && energy <= h->emax[k])
+          value = h->swf[k] * (1.0 + h->emin[k - 1] / energy) * interpolate(k - 1, k, energy + h->emin[k - 1]) * h->reldens[k];
       } else if (energy >= h->emin[k] && energy <= h->emax[k]) {          // BMC.C:597-603
-        const int64_t o = h->xs_off[k], n = h->xs_off[k + 1] - o;
-        value = lin_interp(h->xs_e.data() + o, h->xs_v.data() + o, n, energy) * h->reldens[k];
+        value = interpolate(k, k, energy) * h->reldens[k];
       }
       acc += value;
       row[k] = acc;
