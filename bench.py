@@ -551,7 +551,9 @@ def main():
                 line["time_to_3sigma"] = t3s()
                 fm = t3s("--fast-mode")
                 line["time_to_3sigma"]["fast_mode"] = dict(value=fm["value"], unit="s", runs=fm.get("runs"), within_3sigma=fm["within_3sigma"], worst_deviation_sigma=fm["worst_deviation_sigma"], worst_parameter=fm["worst_parameter"],
-                                                           events=fm["events"], note="numericsMC.fastMode: true (per-energy-band trial frequencies; not a reference key)")
+                                                           events=fm["events"], note="numericsMC.fastMode: true (per-energy-band trial frequencies; not a reference key).  within_3sigma is the verdict on the WORST of the 41 "
+                                                                "parameters for this one fixed seed: by chance alone it exceeds 3 sigma in about one run out of ten in either mode (seed scan: "
+                                                                "profiles/r2_time_to_3sigma_seeds.txt); fast mode is validated against the reference on 8 ensemble goldens in tests/test_gpu_ensemble.py")
             except Exception as ex:
                 line["time_to_3sigma"] = dict(value=None, error=str(ex))
         emit(line)
